@@ -1,0 +1,145 @@
+/*
+ * lentil_b200 — C-ABI of the B200-native far-field diffraction path.
+ *
+ * Drop-in boundary for the hot path of andykee/lentil (v0.8.8).  lentil has no FFI of its
+ * own: its "operator API" for this path is a handful of Python callables.  Every entry point
+ * below names the reference interface (file:line under the lentil source tree) it replaces;
+ * the Python shim in lentil_b200/ binds them with ctypes.
+ *
+ * Conventions
+ *   - plain C, no CUDA/torch types: device pointers travel as void*, streams as void*
+ *     (a cudaStream_t; NULL = the legacy default stream).
+ *   - complex128 = interleaved (re, im) doubles, exactly numpy's layout.  Leading dimensions
+ *     (ld*) are in ELEMENTS (complex elements for complex arrays).
+ *   - every function returns 0 on success, non-zero on failure; lfd_last_error() then holds a
+ *     message (thread-local).  No exceptions cross the ABI.  Nothing allocates behind the
+ *     caller's back except the lfd_ctx_* host-buffer convenience layer.
+ *   - "dev" in a name/param = device memory; "host" = host memory.
+ */
+#ifndef LENTIL_B200_H
+#define LENTIL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LFD_ABI_VERSION 1
+
+/* ---- errors / introspection ------------------------------------------------------------ */
+int         lfd_abi_version(void);
+const char *lfd_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py gpu_launches) */
+uint64_t    lfd_launch_count(void);
+/* device properties the host planner needs: [0]=SM count, [1]=cc major, [2]=cc minor */
+int         lfd_device_info(int device, int *out3);
+
+/* ---- K2a: matrix Fourier transform, complex128 ------------------------------------------
+ * One plane of  F = E1 . f . E2 . sqrt|ar*ac|   with
+ *   E1[k,i] = exp(-2 pi i ar (R_i + off_r)(U_k - shift_r)),  R_i = i - floor(m/2), U_k = k - floor(M/2)
+ *   E2[j,l] = exp(-2 pi i ac (S_j + off_c)(V_l - shift_c))
+ * replaces lentil/fourier.py:5-103 (dft2) with E1/E2 of :106-121 generated on the fly, and
+ * lentil/fourier.py:124-198 (idft2 = conj(dft2(conj F))/F.size) when inverse != 0.
+ */
+typedef struct lfd_mft_desc {
+    const void *f;        /* dev, complex128 m x n, row-major                        */
+    int64_t     ldf;      /* elements between rows of f (>= n)                        */
+    void       *out;      /* dev, complex128 M x N, row-major; may NOT alias f        */
+    int64_t     ldo;      /* elements between rows of out (>= N)                      */
+    int32_t     m, n;     /* input shape                                              */
+    int32_t     M, N;     /* output shape                                             */
+    double      alpha_r, alpha_c;
+    double      shift_r, shift_c;   /* output-plane shift of the DC pixel (pixels)     */
+    double      off_r, off_c;       /* input-plane offset (pixels)                     */
+    int32_t     unitary;            /* fourier.py:100-101                              */
+    int32_t     inverse;            /* 0: dft2, 1: idft2 semantics                     */
+} lfd_mft_desc;
+
+/* bytes of device workspace lfd_mft_c128_batched needs for `count` planes whose largest
+ * intermediate is max over planes of (n * M) complex elements */
+size_t lfd_mft_workspace_bytes(const lfd_mft_desc *descs_host, int count);
+
+/* run `count` independent planes (descriptors in HOST memory, data in device memory) */
+int lfd_mft_c128_batched(const lfd_mft_desc *descs_host, int count,
+                         void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* single plane convenience (same as count == 1) */
+int lfd_mft_c128(const lfd_mft_desc *desc_host, void *workspace_dev, size_t workspace_bytes,
+                 void *stream);
+
+/* ---- K1: pupil prep ------------------------------------------------------------------
+ * For each wavelength w and segment s:  out_{w,s}[r,c] = amp[r,c] * mask_s[r,c] *
+ * exp(+2 pi i opd[r,c] / lambda_w)  over the segment's bounding box.
+ * replaces the phasor build in lentil/plane.py:494-510 (Plane.__mul__) for array operands.
+ */
+typedef struct lfd_segment {
+    int32_t r0, c0;      /* upper-left corner of the bbox in the pupil array            */
+    int32_t h, w;        /* bbox shape                                                  */
+    int32_t mask_index;  /* which mask plane (0 for a 2-D mask)                         */
+    int32_t pad_;
+    int64_t out_offset;  /* element offset of this segment's (h x w, ld = w) tile inside
+                            one wavelength's output block                               */
+} lfd_segment;
+
+int lfd_pupil_prep(const double *amp_dev, const double *opd_dev, /* n_r x n_c, row-major */
+                   const uint8_t *mask_dev,                       /* nmask x n_r x n_c, 0/1; NULL = all ones */
+                   int32_t n_r, int32_t n_c,
+                   const lfd_segment *segs_host, int32_t nseg,
+                   const double *wavelengths_host, int32_t nlam,
+                   void *out_dev,               /* complex128, nlam blocks              */
+                   int64_t out_lam_stride,      /* elements between wavelength blocks   */
+                   void *stream);
+
+/* ---- K3: coherent merge + |E|^2 accumulate ---------------------------------------------
+ * I[r,c] += sum over groups g of  weight_g * | sum over windows v in g covering (r,c) of E_v |^2
+ * replaces lentil/field.py:231-305 (insert), :308-346 (merge), :413-461 (reduce) and
+ * lentil/wavefront.py:114-165 (intensity / insert).  Owner-computes: one thread per output
+ * pixel, groups visited in order, so results are run-to-run bit-identical.
+ */
+typedef struct lfd_window {
+    const void *E;       /* dev complex128 h x w                                          */
+    int64_t     ld;      /* elements between rows                                         */
+    int32_t     h, w;
+    int32_t     r0, c0;  /* position of E[0,0] in the output image (may be negative/clipped) */
+    int32_t     group;   /* windows with equal group are summed coherently; groups must be
+                            contiguous and non-decreasing in the array                    */
+    int32_t     pad_;
+    double      weight;  /* weight of the group (taken from its first window)             */
+} lfd_window;
+
+int lfd_accum_intensity(const lfd_window *wins_host, int32_t nwin,
+                        double *I_dev, int32_t H, int32_t W, int64_t ldI,
+                        void *scratch_dev, size_t scratch_bytes, /* >= nwin*sizeof(lfd_window) */
+                        void *stream);
+
+/* complex (field) insert:  out[r,c] += weight * E_v  — replaces field.py:303-304 / wavefront.py:101-112 */
+int lfd_accum_field(const lfd_window *wins_host, int32_t nwin,
+                    void *out_dev, int32_t H, int32_t W, int64_t ldo,
+                    void *scratch_dev, size_t scratch_bytes, void *stream);
+
+/* ---- host-buffer convenience layer (what bench.py's e2e leg and the numpy shim call) ------
+ * A context owns a device workspace, pinned staging buffers and one stream on `device`.
+ */
+typedef struct lfd_ctx lfd_ctx;
+lfd_ctx *lfd_ctx_create(int device);
+void     lfd_ctx_destroy(lfd_ctx *ctx);
+
+/* dft2 / idft2 with numpy (host) buffers in and out: H2D, K2a, D2H, synchronises.
+ * `f_host` m x n complex128 (ldf elements), `out_host` M x N complex128 (ldo elements);
+ * out_host may alias f_host (tests/test_fourier.py:97-101). */
+int lfd_ctx_dft2_host(lfd_ctx *ctx, const void *f_host, int64_t ldf, int32_t m, int32_t n,
+                      double alpha_r, double alpha_c, int32_t M, int32_t N,
+                      double shift_r, double shift_c, double off_r, double off_c,
+                      int32_t unitary, int32_t inverse, void *out_host, int64_t ldo);
+
+/* ---- diagnostics --------------------------------------------------------------------- */
+/* DMMA.8x8x4 / DFMA issue-rate probe on the current device: out[0] = DMMA TFLOP/s,
+ * out[1] = DFMA TFLOP/s, out[2] = SM clock (MHz) seen by the probe. */
+int lfd_probe_fp64(double *out3, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LENTIL_B200_H */

@@ -1,0 +1,97 @@
+"""ctypes binding of liblentil_b200.so (the C ABI declared in include/lentil_b200.h).
+
+The library is the product: there is no CPU fallback.  Importing this module never touches the
+GPU; the first call that needs the library loads it and raises if it is missing.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblentil_b200.so")
+
+_lib = None
+
+
+class LfdError(RuntimeError):
+    pass
+
+
+class MftDesc(C.Structure):
+    """struct lfd_mft_desc"""
+    _fields_ = [
+        ("f", C.c_void_p), ("ldf", C.c_int64),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+        ("m", C.c_int32), ("n", C.c_int32), ("M", C.c_int32), ("N", C.c_int32),
+        ("alpha_r", C.c_double), ("alpha_c", C.c_double),
+        ("shift_r", C.c_double), ("shift_c", C.c_double),
+        ("off_r", C.c_double), ("off_c", C.c_double),
+        ("unitary", C.c_int32), ("inverse", C.c_int32),
+    ]
+
+
+class Segment(C.Structure):
+    """struct lfd_segment"""
+    _fields_ = [
+        ("r0", C.c_int32), ("c0", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+        ("mask_index", C.c_int32), ("pad_", C.c_int32), ("out_offset", C.c_int64),
+    ]
+
+
+class Window(C.Structure):
+    """struct lfd_window"""
+    _fields_ = [
+        ("E", C.c_void_p), ("ld", C.c_int64),
+        ("h", C.c_int32), ("w", C.c_int32), ("r0", C.c_int32), ("c0", C.c_int32),
+        ("group", C.c_int32), ("pad_", C.c_int32), ("weight", C.c_double),
+    ]
+
+
+# name -> (restype, argtypes); the list doubles as the export manifest the CPU tests check
+SIGNATURES = {
+    "lfd_abi_version": (C.c_int, []),
+    "lfd_last_error": (C.c_char_p, []),
+    "lfd_launch_count": (C.c_uint64, []),
+    "lfd_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
+    "lfd_mft_workspace_bytes": (C.c_size_t, [C.POINTER(MftDesc), C.c_int]),
+    "lfd_mft_c128_batched": (C.c_int, [C.POINTER(MftDesc), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "lfd_mft_c128": (C.c_int, [C.POINTER(MftDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "lfd_pupil_prep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                 C.POINTER(Segment), C.c_int32, C.POINTER(C.c_double), C.c_int32,
+                                 C.c_void_p, C.c_int64, C.c_void_p]),
+    "lfd_accum_intensity": (C.c_int, [C.POINTER(Window), C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                      C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "lfd_accum_field": (C.c_int, [C.POINTER(Window), C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                  C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "lfd_ctx_create": (C.c_void_p, [C.c_int]),
+    "lfd_ctx_destroy": (None, [C.c_void_p]),
+    "lfd_ctx_dft2_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                    C.c_double, C.c_double, C.c_int32, C.c_int32,
+                                    C.c_double, C.c_double, C.c_double, C.c_double,
+                                    C.c_int32, C.c_int32, C.c_void_p, C.c_int64]),
+    "lfd_probe_fp64": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
+}
+
+
+def lib():
+    """Load (once) and return the shared library.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LfdError(
+                f"{LIB_PATH} is missing: build it with `python -m lentil_b200.csrc.build` "
+                "(lentil_b200 has no CPU fallback)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        if handle.lfd_abi_version() != 1:
+            raise LfdError("liblentil_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().lfd_last_error().decode("utf-8", "replace")
+        raise LfdError(f"{what or 'lentil_b200'} failed (rc={rc}): {msg}")

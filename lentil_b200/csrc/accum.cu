@@ -1,0 +1,114 @@
+// K3 — coherent merge of overlapping output windows + |E|^2 (or complex) accumulate.
+//
+// Replaces lentil/field.py:231-305 (insert: place a window at out//2 - shape//2 + offset, clip,
+// `out[slc] += |E**2| * weight`), lentil/field.py:308-346 + :413-461 (reduce/merge: overlapping
+// windows of one wavefront are summed as complex fields first) and lentil/wavefront.py:114-165
+// (intensity / insert / field).
+//
+// Owner-computes: one thread per output pixel walks the window list in order, summing the
+// complex fields of a group (= one wavefront: all segments at one wavelength / field point),
+// squaring at group boundaries and accumulating weight * |sum|^2.  A pixel no window covers
+// gets += 0, which is what merging into a zero-filled bounding box produces in the reference.
+// No atomics, so the result is independent of scheduling.  HBM-bound: 16 B read per covered
+// (pixel, window), one 8 B read-modify-write per pixel.
+#include "lfd_common.cuh"
+
+namespace lfd {
+
+constexpr int WIN_CHUNK = 64;
+
+template <bool INTENSITY>
+__global__ void __launch_bounds__(256)
+accum_kernel(const lfd_window *__restrict__ wins, int nwin, double *__restrict__ out, int H, int W,
+             long long ldo) {
+    __shared__ lfd_window sw[WIN_CHUNK];
+    const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int r = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const bool live = (r < H) && (c < W);
+
+    double acc_r = 0.0, acc_i = 0.0;   // INTENSITY: acc_r only
+    double sr = 0.0, si = 0.0, wgt = 0.0;
+    int group = INT_MIN;
+
+    for (int v0 = 0; v0 < nwin; v0 += WIN_CHUNK) {
+        int nv = min(WIN_CHUNK, nwin - v0);
+        __syncthreads();
+        // cooperative copy of the descriptors (48 B each) as 8-byte words
+        for (int i = threadIdx.x; i < nv * (int)(sizeof(lfd_window) / 8); i += blockDim.x)
+            reinterpret_cast<unsigned long long *>(sw)[i] =
+                reinterpret_cast<const unsigned long long *>(wins + v0)[i];
+        __syncthreads();
+        if (!live) continue;
+        for (int v = 0; v < nv; ++v) {
+            const lfd_window &w = sw[v];
+            if (INTENSITY && w.group != group) {
+                acc_r += wgt * (sr * sr + si * si);
+                sr = si = 0.0;
+                group = w.group;
+                wgt = w.weight;
+            }
+            int rr = r - w.r0, cc = c - w.c0;
+            if (rr >= 0 && rr < w.h && cc >= 0 && cc < w.w) {
+                double2 e = reinterpret_cast<const double2 *>(w.E)[(long long)rr * w.ld + cc];
+                if (INTENSITY) {
+                    sr += e.x;
+                    si += e.y;
+                } else {
+                    acc_r += w.weight * e.x;
+                    acc_i += w.weight * e.y;
+                }
+            }
+        }
+    }
+    if (!live) return;
+    if (INTENSITY) {
+        acc_r += wgt * (sr * sr + si * si);
+        out[(long long)r * ldo + c] += acc_r;
+    } else {
+        double2 *o = reinterpret_cast<double2 *>(out) + (long long)r * ldo + c;
+        double2 cur = *o;
+        *o = make_double2(cur.x + acc_r, cur.y + acc_i);
+    }
+}
+
+static int launch_accum(bool intensity, const lfd_window *wins, int32_t nwin, void *out, int32_t H,
+                        int32_t W, int64_t ldo, void *scratch, size_t scratch_bytes,
+                        cudaStream_t stream) {
+    if (nwin == 0) return 0;
+    LFD_REQUIRE(wins && out && scratch, "lfd_accum: NULL argument");
+    LFD_REQUIRE(H > 0 && W > 0 && ldo >= W, "lfd_accum: bad output shape");
+    LFD_REQUIRE(scratch_bytes >= (size_t)nwin * sizeof(lfd_window),
+                "lfd_accum: scratch too small (%zu < %zu)", scratch_bytes,
+                (size_t)nwin * sizeof(lfd_window));
+    for (int v = 0; v < nwin; ++v) {
+        LFD_REQUIRE(wins[v].E && wins[v].h > 0 && wins[v].w > 0 && wins[v].ld >= wins[v].w,
+                    "lfd_accum: window %d malformed", v);
+        LFD_REQUIRE(v == 0 || wins[v].group >= wins[v - 1].group,
+                    "lfd_accum: window groups must be non-decreasing");
+    }
+    LFD_CUDA_OK(cudaMemcpyAsync(scratch, wins, (size_t)nwin * sizeof(lfd_window),
+                                cudaMemcpyHostToDevice, stream));
+    dim3 grid((W + 63) / 64, (H + 3) / 4);
+    if (intensity)
+        accum_kernel<true><<<grid, 256, 0, stream>>>((const lfd_window *)scratch, nwin, (double *)out, H, W, ldo);
+    else
+        accum_kernel<false><<<grid, 256, 0, stream>>>((const lfd_window *)scratch, nwin, (double *)out, H, W, ldo);
+    LFD_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+}  // namespace lfd
+
+extern "C" int lfd_accum_intensity(const lfd_window *wins, int32_t nwin, double *I, int32_t H,
+                                   int32_t W, int64_t ldI, void *scratch, size_t scratch_bytes,
+                                   void *stream) {
+    return lfd::launch_accum(true, wins, nwin, I, H, W, ldI, scratch, scratch_bytes,
+                             (cudaStream_t)stream);
+}
+
+extern "C" int lfd_accum_field(const lfd_window *wins, int32_t nwin, void *out, int32_t H, int32_t W,
+                               int64_t ldo, void *scratch, size_t scratch_bytes, void *stream) {
+    return lfd::launch_accum(false, wins, nwin, out, H, W, ldo, scratch, scratch_bytes,
+                             (cudaStream_t)stream);
+}

@@ -1,0 +1,84 @@
+// Shared device/host helpers for the lentil_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "../../include/lentil_b200.h"
+
+namespace lfd {
+
+// ---- error plumbing (no exceptions across the C ABI) ------------------------------------
+void set_error(const char *fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define LFD_CUDA_OK(expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t e__ = (expr);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            lfd::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),         \
+                           __FILE__, __LINE__);                                             \
+            return 1;                                                                       \
+        }                                                                                   \
+    } while (0)
+
+#define LFD_REQUIRE(cond, ...)                                                              \
+    do {                                                                                    \
+        if (!(cond)) {                                                                      \
+            lfd::set_error(__VA_ARGS__);                                                    \
+            return 2;                                                                       \
+        }                                                                                   \
+    } while (0)
+
+// ---- device helpers -------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// exp(sgn * 2 pi i * alpha * x * y): the phase is formed and range-reduced in CYCLES with the
+// rounding error of both products carried along, and only then handed to sincospi.  |phase|
+// reaches 1e2..1e4 rad on this path (SURVEY.md hard part 2), so reducing in radians would
+// throw away 3-4 digits.
+__device__ __forceinline__ void cis_cycles(double alpha, double x, double y, double sgn,
+                                           double &c, double &s) {
+    double p  = x * y;
+    double pe = fma(x, y, -p);
+    double t  = alpha * p;
+    double te = fma(alpha, p, -t) + alpha * pe;
+    double r  = (t - rint(t)) + te;
+    sincospi(2.0 * r, &s, &c);
+    s *= sgn;
+}
+
+__device__ __forceinline__ double neg_f64(double v) {
+    // sign flip on the integer pipe: keeps the FP64 pipe for DMMA
+    return __hiloint2double(__double2hiint(v) ^ 0x80000000, __double2loint(v));
+}
+
+// D(8x8) += A(8x4) * B(4x8), all fp64.  sm_100a lowers every mma.sync f64 shape to this one
+// SASS instruction (DMMA.8x8x4), so it is the native granule.
+//   A: lane holds A[g][t]        (g = lane / 4, t = lane % 4)
+//   B: lane holds B[t][g]
+//   C/D: lane holds D[g][2t], D[g][2t+1]
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d0), "+d"(d1)
+        : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, bool pred) {
+    unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int bytes = pred ? 16 : 0;  // src-size 0 => 16 bytes of zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src),
+                 "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+#endif  // __CUDACC__
+
+}  // namespace lfd
