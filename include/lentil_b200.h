@@ -33,6 +33,9 @@ int         lfd_abi_version(void);
 const char *lfd_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py gpu_launches) */
 uint64_t    lfd_launch_count(void);
+/* sizeof() of the ABI structs as compiled: 0 = lfd_mft_desc, 1 = lfd_segment, 2 = lfd_window
+ * (bindings assert their own layout against these) */
+size_t      lfd_struct_size(int which);
 /* device properties the host planner needs: [0]=SM count, [1]=cc major, [2]=cc minor */
 int         lfd_device_info(int device, int *out3);
 
@@ -118,6 +121,14 @@ int lfd_accum_intensity(const lfd_window *wins_host, int32_t nwin,
 int lfd_accum_field(const lfd_window *wins_host, int32_t nwin,
                     void *out_dev, int32_t H, int32_t W, int64_t ldo,
                     void *scratch_dev, size_t scratch_bytes, void *stream);
+
+/* element-wise product of two complex128 windows times a complex scalar:
+ *   out[r,c] = a[r,c] * b[r,c] * (s_re + i s_im)   (b == NULL: out = a * scalar)
+ * the caller points a/b at the upper-left corner of the rectangle intersection.
+ * replaces the array branch of Field.__mul__, lentil/field.py:130-147. */
+int lfd_field_mul(const void *a_dev, int64_t lda, const void *b_dev, int64_t ldb,
+                  double s_re, double s_im, void *out_dev, int64_t ldo,
+                  int32_t h, int32_t w, void *stream);
 
 /* ---- host-buffer convenience layer (what bench.py's e2e leg and the numpy shim call) ------
  * A context owns a device workspace, pinned staging buffers and one stream on `device`.

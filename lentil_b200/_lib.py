@@ -51,6 +51,7 @@ SIGNATURES = {
     "lfd_abi_version": (C.c_int, []),
     "lfd_last_error": (C.c_char_p, []),
     "lfd_launch_count": (C.c_uint64, []),
+    "lfd_struct_size": (C.c_size_t, [C.c_int]),
     "lfd_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
     "lfd_mft_workspace_bytes": (C.c_size_t, [C.POINTER(MftDesc), C.c_int]),
     "lfd_mft_c128_batched": (C.c_int, [C.POINTER(MftDesc), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -62,6 +63,8 @@ SIGNATURES = {
                                       C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "lfd_accum_field": (C.c_int, [C.POINTER(Window), C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                   C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "lfd_field_mul": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_double, C.c_double,
+                                C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "lfd_ctx_create": (C.c_void_p, [C.c_int]),
     "lfd_ctx_destroy": (None, [C.c_void_p]),
     "lfd_ctx_dft2_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
@@ -87,6 +90,9 @@ def lib():
             fn.argtypes = args
         if handle.lfd_abi_version() != 1:
             raise LfdError("liblentil_b200.so ABI version mismatch")
+        for which, struct in enumerate((MftDesc, Segment, Window)):
+            if handle.lfd_struct_size(which) != C.sizeof(struct):
+                raise LfdError(f"ABI struct layout mismatch for {struct.__name__}")
         _lib = handle
     return _lib
 

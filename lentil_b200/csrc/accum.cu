@@ -98,7 +98,37 @@ static int launch_accum(bool intensity, const lfd_window *wins, int32_t nwin, vo
     return 0;
 }
 
+__global__ void __launch_bounds__(256)
+field_mul_kernel(const double2 *__restrict__ a, long long lda, const double2 *__restrict__ b,
+                 long long ldb, double sr, double si, double2 *__restrict__ out, long long ldo, int h,
+                 int w) {
+    const long long n = (long long)h * w;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+         e += (long long)gridDim.x * blockDim.x) {
+        int r = (int)(e / w), c = (int)(e % w);
+        double2 x = a[r * lda + c];
+        if (b != nullptr) {
+            double2 y = b[r * ldb + c];
+            x = make_double2(x.x * y.x - x.y * y.y, x.x * y.y + x.y * y.x);
+        }
+        out[r * ldo + c] = make_double2(x.x * sr - x.y * si, x.x * si + x.y * sr);
+    }
+}
+
 }  // namespace lfd
+
+extern "C" int lfd_field_mul(const void *a, int64_t lda, const void *b, int64_t ldb, double s_re,
+                             double s_im, void *out, int64_t ldo, int32_t h, int32_t w, void *stream) {
+    LFD_REQUIRE(a && out && h > 0 && w > 0 && lda >= w && ldo >= w && (!b || ldb >= w),
+                "lfd_field_mul: bad arguments");
+    long long n = (long long)h * w, blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    lfd::field_mul_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const double2 *)a, lda, (const double2 *)b, ldb, s_re, s_im, (double2 *)out, ldo, h, w);
+    LFD_CUDA_OK(cudaGetLastError());
+    lfd::count_launch();
+    return 0;
+}
 
 extern "C" int lfd_accum_intensity(const lfd_window *wins, int32_t nwin, double *I, int32_t H,
                                    int32_t W, int64_t ldI, void *scratch, size_t scratch_bytes,

@@ -25,6 +25,15 @@ extern "C" int lfd_abi_version(void) { return LFD_ABI_VERSION; }
 extern "C" const char *lfd_last_error(void) { return g_err; }
 extern "C" uint64_t lfd_launch_count(void) { return g_launches.load(); }
 
+extern "C" size_t lfd_struct_size(int which) {
+    switch (which) {
+        case 0: return sizeof(lfd_mft_desc);
+        case 1: return sizeof(lfd_segment);
+        case 2: return sizeof(lfd_window);
+        default: return 0;
+    }
+}
+
 extern "C" int lfd_device_info(int device, int *out3) {
     LFD_REQUIRE(out3 != nullptr, "lfd_device_info: NULL output");
     cudaDeviceProp p;

@@ -1,0 +1,91 @@
+"""Device plumbing: PyTorch supplies device memory, streams and pinned staging; every kernel is
+ours and is reached through the C ABI (lentil_b200._lib).  There is no CPU fallback: calling a
+compute entry point without a CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_device = None
+
+
+class NoDeviceError(RuntimeError):
+    pass
+
+
+def device():
+    """The CUDA device this process computes on (cuda:LOCAL_RANK unless set_device was called)."""
+    global _device
+    if _device is None:
+        if not torch.cuda.is_available():
+            raise NoDeviceError("lentil_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        _device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")) % torch.cuda.device_count())
+        torch.cuda.set_device(_device)
+        _lib.lib()  # fail now, loudly, if the CUDA library has not been built
+    return _device
+
+
+def set_device(index):
+    global _device
+    if not torch.cuda.is_available():
+        raise NoDeviceError("lentil_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    _device = torch.device("cuda", int(index))
+    torch.cuda.set_device(_device)
+    _lib.lib()
+    return _device
+
+
+def stream_ptr():
+    """cudaStream_t of torch's current stream, as an int for ctypes."""
+    return torch.cuda.current_stream(device()).cuda_stream
+
+
+def is_dev(x):
+    return isinstance(x, torch.Tensor)
+
+
+def empty_c128(*shape):
+    return torch.empty(*shape, dtype=torch.complex128, device=device())
+
+
+def zeros_f64(*shape):
+    return torch.zeros(*shape, dtype=torch.float64, device=device())
+
+
+def empty_bytes(nbytes):
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device())
+
+
+def to_dev(arr, dtype=None):
+    """Host array -> device tensor (H2D on the current stream; pinned sources go async)."""
+    a = np.ascontiguousarray(arr, dtype=dtype)
+    t = torch.from_numpy(a) if a.flags.writeable else torch.from_numpy(a.copy())
+    return t.to(device(), non_blocking=True)
+
+
+def to_host(t):
+    """Device tensor -> numpy (D2H, synchronises the current stream)."""
+    return t.detach().cpu().numpy()
+
+
+def ld_of(t):
+    """Leading dimension (elements between rows) of a 2-D device array with unit column stride."""
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise ValueError("device field must be 2-D with contiguous rows")
+    return int(t.stride(0)) if t.shape[0] > 1 else int(max(t.shape[1], t.stride(0)))
+
+
+def launch_count():
+    return int(_lib.lib().lfd_launch_count())
+
+
+def probe_fp64(iters=20000):
+    """Measured DMMA / DFMA issue rates of the current device (TFLOP/s) and its SM clock."""
+    device()
+    out = (C.c_double * 3)()
+    _lib.check(_lib.lib().lfd_probe_fp64(out, int(iters)), "lfd_probe_fp64")
+    return {"dmma_tflops": out[0], "dfma_tflops": out[1], "clock_mhz": out[2]}

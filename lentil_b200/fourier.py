@@ -1,0 +1,84 @@
+"""Matrix-triple-product DFT with independent input/output shape, sampling, sub-pixel output
+shift and integer input offset — same call surface as lentil/fourier.py (dft2 :5-103, idft2
+:124-198), executed by K2a (lfd_mft_c128, FP64 DMMA with on-the-fly twiddles).
+
+    F[k,l] = sqrt|ar ac| * sum_ij  e^{-2 pi i ar (R_i+off_r)(U_k-shift_r)} f[i,j]
+                                   e^{-2 pi i ac (S_j+off_c)(V_l-shift_c)}
+    R_i = i - floor(m/2), S_j = j - floor(n/2), U_k = k - floor(M/2), V_l = l - floor(N/2)
+"""
+import numpy as np
+
+from . import _lib, device
+
+
+def _pair(v):
+    a, b = np.broadcast_to(v, (2,))
+    return a, b
+
+
+def mft_descriptor(desc, f_dev, out_dev, alpha, shift, offset, unitary=True, inverse=False):
+    """Fill one lfd_mft_desc for device arrays `f_dev` (m x n) -> `out_dev` (M x N)."""
+    ar, ac = _pair(alpha)
+    sr, sc = _pair(shift)
+    orow, ocol = _pair(offset)
+    desc.f, desc.ldf = f_dev.data_ptr(), device.ld_of(f_dev)
+    desc.out, desc.ldo = out_dev.data_ptr(), device.ld_of(out_dev)
+    desc.m, desc.n = int(f_dev.shape[0]), int(f_dev.shape[1])
+    desc.M, desc.N = int(out_dev.shape[0]), int(out_dev.shape[1])
+    desc.alpha_r, desc.alpha_c = float(ar), float(ac)
+    desc.shift_r, desc.shift_c = float(sr), float(sc)
+    desc.off_r, desc.off_c = float(orow), float(ocol)
+    desc.unitary, desc.inverse = int(bool(unitary)), int(bool(inverse))
+    return desc
+
+
+def run_mft(descs, count):
+    """Launch a batch of planes on the current stream with a torch-owned workspace."""
+    L = _lib.lib()
+    need = L.lfd_mft_workspace_bytes(descs, count)
+    ws = device.empty_bytes(need)
+    _lib.check(L.lfd_mft_c128_batched(descs, count, ws.data_ptr(), need, device.stream_ptr()),
+               "lfd_mft_c128_batched")
+    return ws
+
+
+def dft2_dev(f_dev, alpha, shape=None, shift=(0, 0), offset=(0, 0), unitary=True, inverse=False,
+             out=None):
+    """dft2 on device arrays; returns a complex128 device tensor (no host transfer)."""
+    m, n = int(f_dev.shape[0]), int(f_dev.shape[1])
+    M, N = (m, n) if shape is None else (int(v) for v in _pair(shape))
+    if out is None:
+        out = device.empty_c128(M, N)
+    descs = (_lib.MftDesc * 1)()
+    mft_descriptor(descs[0], f_dev, out, alpha, shift, offset, unitary, inverse)
+    run_mft(descs, 1)
+    return out
+
+
+def _transform(f, alpha, shape, shift, offset, unitary, out, inverse):
+    if out is not None and not np.can_cast(complex, out.dtype):
+        raise TypeError(f"Cannot cast complex output to dtype('{out.dtype}')")
+    f = np.asarray(f)
+    m, n = f.shape
+    f_dev = device.to_dev(f, dtype=np.complex128)
+    F = device.to_host(dft2_dev(f_dev, alpha, shape, shift, offset, unitary, inverse))
+    if out is not None:
+        out[...] = F
+        return out
+    return F
+
+
+def dft2(f, alpha, shape=None, shift=(0, 0), offset=(0, 0), unitary=True, out=None):
+    """2-D discrete Fourier transform by matrix triple product (lentil/fourier.py:5-103).
+
+    f : array_like (m, n); alpha : float or (row, col); shape : int or (M, N), default f.shape;
+    shift : output-plane DC shift in pixels (r, c), may be fractional; offset : input-plane
+    offset in pixels (r, c); unitary : scale by sqrt|alpha_r alpha_c|; out : optional result
+    array (must accept complex, else TypeError; may alias f)."""
+    return _transform(f, alpha, shape, shift, offset, unitary, out, inverse=False)
+
+
+def idft2(F, alpha, shape=None, shift=(0, 0), unitary=True, out=None):
+    """Inverse transform, conj(dft2(conj F)) / F.size (lentil/fourier.py:124-198): the
+    conjugations fold into the twiddle sign, the division into the output scale."""
+    return _transform(F, alpha, shape, shift, (0, 0), unitary, out, inverse=True)

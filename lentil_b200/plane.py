@@ -1,0 +1,439 @@
+"""Planes: amplitude / OPD / mask containers whose product with a Wavefront builds the complex
+phasor amp * exp(2 pi i opd / lambda) on each segment's bounding box.
+
+Mirror of the hot part of lentil/plane.py: _PlaneBase :19-396 (properties, freeze/thaw),
+Plane :414-611 (__mul__ :477-516, fit_tilt :564-611), ptype table :634-668, _plane_slice
+:671-705, Pupil :708-771, Image :774-820, Tilt :884-923.  The phasor build runs on the device
+(K1, lfd_pupil_prep); slicing, tilt bookkeeping and the ptype rules are host metadata.
+
+Out of scope here: rescale/resample, DispersiveTilt/Grism, Rotate/Flip.
+"""
+import copy
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, device, helper
+import importlib
+_pt = importlib.import_module(".ptype", __package__)  # the package attribute `ptype` is the factory function
+from .field import Field
+
+
+class _PlaneBase:
+    """Low-level plane interface (lentil/plane.py:19-396): user subclasses may override
+    ``__amp__``, ``__opd__`` and ``__mask__``; they are called on the host on every access
+    unless the plane is frozen."""
+
+    def __new__(cls, *args, **kwargs):
+        self = super().__new__(cls)
+        self._amplitude = np.array(1)
+        self._opd = np.array(0)
+        self._mask = None
+        self._pixelscale = None
+        self._ptype = _pt.ptype(None)
+        self._diameter = None
+        self.tilt = []
+        self._frozen = False
+        self._dev_cache = None
+        self.__freeze_attrs__ = ['amplitude', 'opd']
+        return self
+
+    def __repr__(self):
+        return f'{self.__class__.__name__}()'
+
+    def __amp__(self):
+        return self._amplitude
+
+    def __mask__(self):
+        if self._mask is None:
+            return np.copy(self.amplitude).astype(bool)
+        return self._mask
+
+    def __opd__(self):
+        return self._opd
+
+    def __mul__(self, wavefront):
+        raise NotImplementedError
+
+    def __rmul__(self, other):
+        return self.__mul__(other)
+
+    @property
+    def ptype(self):
+        return self._ptype
+
+    @ptype.setter
+    def ptype(self, value):
+        self._ptype = _pt.ptype(value)
+
+    @property
+    def amplitude(self):
+        """Electric field amplitude transmission (cached while frozen)."""
+        return self._amplitude if self.frozen else self.__amp__()
+
+    @amplitude.setter
+    def amplitude(self, value):
+        if self.frozen:
+            raise RuntimeError('Can\'t set amplitude while Plane is frozen')
+        self._amplitude = np.asarray(value)
+
+    @property
+    def opd(self):
+        """Optical path difference (cached while frozen)."""
+        return self._opd if self.frozen else self.__opd__()
+
+    @opd.setter
+    def opd(self, value):
+        if self.frozen:
+            raise RuntimeError('Can\'t set opd while Plane is frozen')
+        self._opd = np.asarray(value)
+
+    @property
+    def mask(self):
+        return self.__mask__()
+
+    @property
+    def global_mask(self):
+        return self.mask if self.size < 2 else np.sum(self.mask, axis=0)
+
+    @property
+    def pixelscale(self):
+        return self._pixelscale
+
+    @property
+    def diameter(self):
+        if self._diameter is None:
+            rmin, rmax, cmin, cmax = helper.boundary(self.global_mask)
+            return np.max(np.max((rmax - rmin, cmax - cmin)) * np.asarray(self.pixelscale))
+        return self._diameter
+
+    @property
+    def shape(self):
+        m = self.mask
+        return m.shape if self.size == 1 else (m.shape[1], m.shape[2])
+
+    @property
+    def size(self):
+        m = self.mask
+        return 1 if m.ndim in (0, 1, 2) else m.shape[0]
+
+    @property
+    def frozen(self):
+        return self._frozen
+
+    def freeze(self, inplace=True):
+        """Cache the attributes named in ``__freeze_attrs__`` (lentil/plane.py:218-257).  On the
+        device this is also what keeps amplitude / OPD / mask resident in HBM across a
+        wavelength loop: a frozen plane uploads them once."""
+        if self.frozen:
+            raise RuntimeError('Plane is already frozen. Call thaw() to unfreeze.')
+        target = self if inplace else copy.deepcopy(self)
+        for attr in target.__freeze_attrs__:
+            setattr(target, f'_{attr}', getattr(target, attr))
+        target._frozen = True
+        target._dev_cache = None
+        if not inplace:
+            return target
+
+    def thaw(self):
+        self._frozen = False
+        self._dev_cache = None
+
+    def __deepcopy__(self, memo):
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            setattr(new, k, None if k == '_dev_cache' else copy.deepcopy(v, memo))
+        return new
+
+
+def _mul_pixelscale(a, b):
+    """Pixelscale of a wavefront-plane product (lentil/plane.py:614-629)."""
+    a = None if a is None else np.broadcast_to(a, (2,))
+    b = None if b is None else np.broadcast_to(b, (2,))
+    if a is None:
+        return b
+    if b is None:
+        return a
+    if all(a == b):
+        return a
+    raise ValueError(f"can't multiply with inconsistent pixelscales: {a} != {b}")
+
+
+# wavefront ptype -> {plane ptype: result ptype}; a missing plane ptype forbids the product
+# (lentil/plane.py:634-668)
+_MUL_PTYPE = {
+    _pt.none: {_pt.none: _pt.none, _pt.pupil: _pt.pupil, _pt.image: _pt.image,
+               _pt.tilt: _pt.none, _pt.transform: _pt.none},
+    _pt.pupil: {_pt.pupil: _pt.pupil, _pt.tilt: _pt.pupil, _pt.transform: _pt.pupil},
+    _pt.image: {_pt.image: _pt.image, _pt.tilt: _pt.pupil, _pt.transform: _pt.pupil},
+}
+
+
+def _plane_slice(mask):
+    """Bounding-box slices of each segment of `mask` (lentil/plane.py:671-705)."""
+    if mask is None or mask.ndim < 2:
+        return [Ellipsis]
+    if mask.ndim == 2:
+        return [helper.boundary_slice(mask)]
+    if mask.ndim == 3:
+        return [helper.boundary_slice(m) for m in mask]
+    raise ValueError('mask has invalid dimensions')
+
+
+class Plane(_PlaneBase):
+    """Finite geometric plane (lentil/plane.py:414-475).  Same constructor as the reference,
+    including the ``amp`` alias."""
+
+    def __init__(self, amplitude=None, opd=None, mask=None, pixelscale=None, diameter=None,
+                 ptype=None, **kwargs):
+        if 'amp' in kwargs:
+            if amplitude is not None:
+                raise AttributeError("Got both 'amplitude' and 'amp', which are aliases of one another")
+            amplitude = kwargs['amp']
+        if amplitude is not None:
+            self._amplitude = np.asarray(amplitude)
+        if opd is not None:
+            self._opd = np.asarray(opd)
+        if mask is not None:
+            self._mask = np.asarray(mask)
+        if pixelscale is not None:
+            self._pixelscale = np.broadcast_to(pixelscale, (2,))
+        if diameter is not None:
+            self._diameter = diameter
+        if ptype is not None:
+            self._ptype = _pt.ptype(ptype)
+
+    # ---- device-side operands -------------------------------------------------------------------
+    def _operands(self):
+        """Host metadata + device copies of (amplitude, opd, mask) for K1.  Uploaded once per
+        multiply, or once per freeze() when the plane is frozen."""
+        if self.frozen and self._dev_cache is not None:
+            return self._dev_cache
+        amp, opd, mask = np.asarray(self.amplitude), np.asarray(self.opd), np.asarray(self.mask)
+        nseg = 1 if mask.ndim < 3 else mask.shape[0]
+        shape = tuple(mask.shape) if nseg == 1 else tuple(mask.shape[1:])
+        slices = _plane_slice(mask)
+        ops = {'nseg': nseg, 'shape': shape, 'slices': slices, 'scalar': None}
+        if amp.size == 1 and opd.size == 1:
+            ops['scalar'] = (amp, opd)
+        else:
+            if len(shape) != 2:
+                raise ValueError('array amplitude/opd need a 2-D (or 3-D segment) mask')
+            use_mask = amp.size != 1       # plane.py:503 — a scalar amplitude is not masked
+            if use_mask:
+                mk = mask.reshape((nseg,) + shape)
+                binary = mk.dtype == bool or np.all((mk == 0) | (mk == 1))
+                if not binary:
+                    if nseg > 1:
+                        raise NotImplementedError('non-binary segment masks are not supported')
+                    amp, use_mask = amp * mk[0], False
+            ops['amp'] = device.to_dev(np.broadcast_to(amp, shape), dtype=np.float64)
+            ops['opd'] = device.to_dev(np.broadcast_to(opd, shape), dtype=np.float64)
+            ops['mask'] = device.to_dev(mk.astype(np.uint8)) if use_mask else None
+            segs = (_lib.Segment * nseg)()
+            total = 0
+            for k, s in enumerate(slices):
+                if s is Ellipsis:
+                    r0, r1, c0, c1 = 0, shape[0], 0, shape[1]
+                else:
+                    r0, r1, c0, c1 = int(s[0].start), int(s[0].stop), int(s[1].start), int(s[1].stop)
+                segs[k].r0, segs[k].c0, segs[k].h, segs[k].w = r0, c0, r1 - r0, c1 - c0
+                segs[k].mask_index = k if nseg > 1 else 0
+                segs[k].out_offset = total
+                total += (r1 - r0) * (c1 - c0)
+            ops['segs'], ops['total'] = segs, total
+            ops['offsets'] = [helper.slice_offset(s, shape) for s in slices]
+        if self.frozen:
+            self._dev_cache = ops
+        return ops
+
+    def _phasors(self, wavelengths):
+        """K1: phasor tiles for a list of wavelengths.  Returns a (nlam, total) complex128 device
+        buffer; segment k of wavelength l is buf[l, off_k : off_k + h_k*w_k] viewed (h_k, w_k)."""
+        ops = self._operands()
+        lam = np.ascontiguousarray(wavelengths, dtype=np.float64).reshape(-1)
+        buf = device.empty_c128(len(lam), ops['total'])
+        rc = _lib.lib().lfd_pupil_prep(
+            ops['amp'].data_ptr(), ops['opd'].data_ptr(),
+            ops['mask'].data_ptr() if ops['mask'] is not None else None,
+            ops['shape'][0], ops['shape'][1], ops['segs'], ops['nseg'],
+            lam.ctypes.data_as(C.POINTER(C.c_double)), len(lam),
+            buf.data_ptr(), ops['total'], device.stream_ptr())
+        _lib.check(rc, "lfd_pupil_prep")
+        return ops, buf
+
+    @staticmethod
+    def _segment_view(ops, buf_row, k):
+        sg = ops['segs'][k]
+        return buf_row[sg.out_offset: sg.out_offset + sg.h * sg.w].view(sg.h, sg.w)
+
+    def __mul__(self, wavefront):
+        """Multiply a wavefront by this plane (lentil/plane.py:477-516): one output Field per
+        (incoming field, segment), phasor = amp[s]*mask_n[s] * exp(2 pi i opd[s] / lambda) at
+        offset slice_offset(s), tilt = [self.tilt[n]] when fit_tilt ran."""
+        from .wavefront import Wavefront
+        wf_pt, my_pt = wavefront.ptype, self.ptype
+        if my_pt not in _MUL_PTYPE[wf_pt]:
+            raise TypeError(f"can't multiply Wavefront with ptype '{wf_pt}' by Plane with ptype '{my_pt}'")
+        ops = self._operands()
+        pixelscale = _mul_pixelscale(self.pixelscale, wavefront.pixelscale)
+        shape = wavefront.shape if ops['shape'] == () else ops['shape']
+        out = Wavefront.empty(wavelength=wavefront.wavelength, pixelscale=pixelscale,
+                              focal_length=wavefront.focal_length, shape=shape,
+                              ptype=_MUL_PTYPE[wf_pt][my_pt])
+        if ops['scalar'] is not None:
+            amp, opd = ops['scalar']
+            value = amp * np.exp(2 * np.pi * 1j * opd / wavefront.wavelength)
+            phasors = [Field(value, pixelscale=self.pixelscale,
+                             offset=helper.slice_offset(s, ops['shape']) if ops['shape'] != () else (0, 0),
+                             tilt=[self.tilt[n]] if self.tilt else [])
+                       for n, s in enumerate(ops['slices'])]
+        else:
+            _, buf = self._phasors([wavefront.wavelength])
+            phasors = [Field(self._segment_view(ops, buf[0], n), pixelscale=self.pixelscale,
+                             offset=ops['offsets'][n], tilt=[self.tilt[n]] if self.tilt else [])
+                       for n in range(ops['nseg'])]
+        for field in wavefront.data:
+            for phasor in phasors:
+                res = field * phasor
+                if res.size > 0:
+                    out.data.append(res)
+        return out
+
+    @property
+    def _slice(self):
+        return _plane_slice(self.mask)
+
+    # ---- tilt fitting (setup-time host code) -----------------------
+    @property
+    def ptt_vector(self):
+        """Piston / x-tilt / y-tilt basis per segment, shape (3*size, npix)
+        (lentil/plane.py:522-562); None for planes without a mask."""
+        if self.shape == () or self.shape is None:
+            return None
+        if self.pixelscale is None:
+            raise ValueError("can't create ptt_vector with pixelscale = ()")
+        ps = np.broadcast_to(self.pixelscale, (2,))
+        r, c = helper.mesh(self.shape)
+        base = np.stack([np.ones(r.size), r.ravel() * ps[0], -c.ravel() * ps[1]])
+        if self.size == 1:
+            return base * self.mask.ravel()
+        return np.concatenate([base * m.ravel() for m in self.mask], axis=0)
+
+    def fit_tilt(self, inplace=False):
+        """Least-squares fit and removal of per-segment tilt from the OPD; the equivalent angles
+        are kept as Tilt objects in ``self.tilt`` (lentil/plane.py:564-611).  Solved on the
+        masked pixels only — rows outside the mask are zero in the reference's design matrix and
+        cannot influence its minimum-norm solution."""
+        plane = self if inplace else copy.deepcopy(self)
+        if plane.shape == () or plane.shape is None or plane.opd.size == 1:
+            return plane
+        if plane.pixelscale is None:
+            raise ValueError("can't create ptt_vector with pixelscale = ()")
+        ps = np.broadcast_to(plane.pixelscale, (2,))
+        r, c = helper.mesh(plane.shape)
+        basis = (np.ones(r.shape), r * ps[0], -c * ps[1])
+        opd = np.array(plane.opd, dtype=float)
+        masks = plane.mask.reshape((plane.size,) + tuple(plane.shape))
+
+        def solve(mk):
+            sel = mk != 0
+            w = mk[sel].astype(float)
+            A = np.stack([b[sel] * w for b in basis], axis=1)
+            return np.linalg.lstsq(A, opd[sel], rcond=None)[0]
+
+        if plane.size == 1:
+            t = solve(masks[0])
+            plane.opd = opd - (basis[1] * masks[0] * t[1] + basis[2] * masks[0] * t[2])
+            plane.tilt.append(Tilt(x=t[1], y=t[2]))
+        else:
+            new = np.zeros_like(opd)
+            ts = []
+            for mk in masks:
+                t = solve(mk)
+                ts.append(t)
+                new += (opd - (basis[1] * mk * t[1] + basis[2] * mk * t[2])) * mk
+            plane.opd = new
+            plane.tilt.extend(Tilt(x=t[1], y=t[2]) for t in ts)
+        plane._dev_cache = None
+        return plane
+
+
+class Pupil(Plane):
+    """Pupil plane (lentil/plane.py:708-771): multiplying hands its focal length to the wavefront."""
+
+    def __new__(cls, *args, **kwargs):
+        self = super().__new__(cls, *args, **kwargs)
+        self._focal_length = None
+        self._ptype = _pt.pupil
+        return self
+
+    def __init__(self, amplitude=None, opd=None, mask=None, pixelscale=None, focal_length=None,
+                 diameter=None, **kwargs):
+        super().__init__(amplitude=amplitude, opd=opd, mask=mask, pixelscale=pixelscale,
+                         diameter=diameter, ptype=_pt.pupil, **kwargs)
+        if focal_length is not None:
+            self._focal_length = focal_length
+
+    def __mul__(self, wavefront):
+        wavefront = super().__mul__(wavefront)
+        wavefront.focal_length = self.focal_length
+        return wavefront
+
+    @property
+    def focal_length(self):
+        return self._focal_length
+
+
+class Image(Plane):
+    """Image plane (lentil/plane.py:774-820)."""
+
+    def __new__(cls, *args, **kwargs):
+        self = super().__new__(cls, *args, **kwargs)
+        self._ptype = _pt.image
+        return self
+
+    def __init__(self, amplitude=None, opd=None, mask=None, pixelscale=None, **kwargs):
+        super().__init__(amplitude=amplitude, opd=opd, mask=mask, pixelscale=pixelscale,
+                         ptype=_pt.image, **kwargs)
+
+    def __mul__(self, wavefront):
+        wavefront = super().__mul__(wavefront)
+        wavefront.ptype = _pt.image
+        return wavefront
+
+    def fit_tilt(self, *args, **kwargs):
+        return self
+
+
+class _TiltBase(Plane):
+    """Planes that act through the tilt interface (lentil/plane.py:823-881): the product
+    appends the plane to every field's tilt list; ``__shift__`` converts it to a shift later."""
+
+    def __new__(cls, *args, **kwargs):
+        self = super().__new__(cls, *args, **kwargs)
+        self._ptype = kwargs['ptype'] if 'ptype' in kwargs else _pt.tilt
+        return self
+
+    def __mul__(self, wavefront):
+        wavefront = super().__mul__(wavefront)
+        for field in wavefront.data:
+            field.tilt.append(self)
+        return wavefront
+
+    def __shift__(self, wavelength, x0, y0, **kwargs):
+        raise NotImplementedError
+
+
+class Tilt(_TiltBase):
+    """Angular tilt (lentil/plane.py:884-923).  `x` is radians about the x-axis, which moves the
+    image along y — hence the swap in the constructor (:898-901)."""
+
+    def __init__(self, x, y, **kwargs):
+        super().__init__(**kwargs)
+        self.x = y
+        self.y = x
+
+    def __shift__(self, xs=0, ys=0, z=0, **kwargs):
+        return xs - (z * self.x), ys - (z * self.y)

@@ -1,0 +1,242 @@
+"""Far-field propagation drivers.
+
+`propagate_dft` keeps the call surface of lentil/propagate.py:147-242: per Field it turns the
+accumulated tilt into a pixel shift, splits it into an integer window move and a sub-pixel DFT
+shift, clips the propagation window against the output (or a detector mask's bounding box) and
+transforms the field onto exactly that window.  All Fields of the wavefront go to the device in
+ONE batched K2a launch pair (lfd_mft_c128_batched).
+
+`propagate_dft_batch` is the loop the reference leaves to user code
+(docs/user/diffraction.rst:154-158) — wavelengths x field points x segments — planned on the
+host and executed as K1 -> K2a -> K3 over whole chunks of planes, with the pupil resident in
+HBM and the PSF stack accumulated on the device.
+"""
+import numpy as np
+
+from . import _lib, device, extent as _extent, helper
+from . import field as _field
+from . import fourier as _fourier
+import importlib
+_pt = importlib.import_module(".ptype", __package__)  # the package attribute `ptype` is the factory function
+from .field import Field
+from .wavefront import Wavefront
+
+
+def _dft_alpha(dx, du, wavelength, z, oversample):
+    """Output sampling in cycles per input pixel per output pixel (lentil/propagate.py:121-123)."""
+    return ((dx[0] * du[0]) / (wavelength * z * oversample),
+            (dx[1] * du[1]) / (wavelength * z * oversample))
+
+
+def _propagate_ptype(ptype, method='fraunhofer'):
+    """pupil <-> image (lentil/propagate.py:263-272)."""
+    if method == 'fraunhofer':
+        if ptype not in (_pt.pupil, _pt.image):
+            raise TypeError("Wavefront must have ptype 'pupil' or 'image'")
+        return _pt.image if ptype == _pt.pupil else _pt.pupil
+
+
+def _mask_shape(x, threshold=0):
+    rmin, rmax, cmin, cmax = helper.boundary(x, threshold)
+    return rmax - rmin + 1, cmax - cmin + 1
+
+
+def _mask_shift(x, threshold=0):
+    """Shift of the masked area's centre from the array centre (lentil/propagate.py:251-260)."""
+    rmin, rmax, cmin, cmax = helper.boundary(x, threshold)
+    return (rmin + (rmax - rmin + 1) // 2 - x.shape[0] // 2,
+            cmin + (cmax - cmin + 1) // 2 - x.shape[1] // 2)
+
+
+def _output_extent(shape_out, mask):
+    """Extent of the region that is actually computed (lentil/propagate.py:182-190)."""
+    if mask is None:
+        return _extent.array_extent(shape_out, shift=(0, 0))
+    mask = np.asarray(mask)
+    if np.all(mask.shape != shape_out):   # same (lenient) test as the reference, propagate.py:184
+        raise ValueError(f'shape mismatch: mask shape {mask.shape} != output shape {tuple(shape_out)}')
+    return _extent.array_extent(_mask_shape(mask), _mask_shift(mask))
+
+
+def plan_window(shift, prop_shape_out, out_extent):
+    """Integer window logic for one Field (lentil/propagate.py:211-230).
+
+    shift : (r, c) float pixel shift of the field centre in the output plane.
+    Returns None when the propagation window misses the output region, else
+    ``(intersect_shape, intersect_shift, dft_shift)``: the window to compute, the offset of the
+    resulting Field, and the shift handed to dft2 (= prop_shift + sub-pixel remainder)."""
+    shift = np.asarray(shift, dtype=float)
+    fix_shift = np.fix(shift)
+    subpx_shift = shift - fix_shift
+    prop_extent = _extent.array_extent(prop_shape_out, fix_shift)
+    if not _extent.intersect(out_extent, prop_extent):
+        return None
+    intersect_shape = _extent.intersection_shape(out_extent, prop_extent)
+    intersect_shift = _extent.intersection_shift(out_extent, prop_extent)
+    intersect_extent = _extent.array_extent(intersect_shape, intersect_shift)
+    prop_shift = (np.array(_extent.array_center(prop_extent))
+                  - np.array(_extent.array_center(intersect_extent)))
+    return intersect_shape, intersect_shift, prop_shift + subpx_shift
+
+
+def propagate_dft(wavefront, pixelscale, shape=None, prop_shape=None, oversample=2, mask=None):
+    """Propagate a Wavefront in the far field with the matrix DFT (lentil/propagate.py:147-242).
+
+    Same parameters, return value and errors as the reference: TypeError unless the wavefront
+    ptype is pupil or image, ValueError on a mask of the wrong shape; returns a NEW Wavefront
+    whose `data` holds one Field per input Field that lands on the output (possibly none)."""
+    ptype_out = _propagate_ptype(wavefront.ptype, method='fraunhofer')
+
+    shape = np.asarray(wavefront.shape) if shape is None else np.broadcast_to(shape, (2,))
+    prop_shape = np.asarray(shape) if prop_shape is None else np.broadcast_to(prop_shape, (2,))
+    shape_out = shape * oversample
+    prop_shape_out = prop_shape * oversample
+    out_extent = _output_extent(shape_out, mask)
+
+    dx = wavefront.pixelscale
+    du = np.broadcast_to(pixelscale, (2,))
+    z = wavefront.focal_length
+
+    out = Wavefront.empty(wavelength=wavefront.wavelength, pixelscale=du / oversample,
+                          focal_length=wavefront.focal_length, shape=shape_out, ptype=ptype_out)
+
+    plans = []
+    for field in wavefront.data:
+        shift = field.shift(z=z, wavelength=wavefront.wavelength, pixelscale=du,
+                            oversample=oversample, indexing='ij')
+        plan = plan_window(shift, prop_shape_out, out_extent)
+        if plan is not None:
+            plans.append((field, plan))
+    if not plans:
+        return out
+
+    alpha = _dft_alpha(dx=dx, du=du, z=z, wavelength=wavefront.wavelength, oversample=oversample)
+    total = sum(int(p[0][0]) * int(p[0][1]) for _, p in plans)
+    buf = device.empty_c128(total)
+    descs = (_lib.MftDesc * len(plans))()
+    pos = 0
+    for k, (field, (ishape, ishift, dshift)) in enumerate(plans):
+        h, w = int(ishape[0]), int(ishape[1])
+        win = buf[pos:pos + h * w].view(h, w)
+        pos += h * w
+        _fourier.mft_descriptor(descs[k], field.dev, win, alpha, dshift, field.offset, unitary=True)
+        out.data.append(Field(data=win, pixelscale=du / oversample, offset=ishift))
+    _fourier.run_mft(descs, len(plans))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# batched driver
+# ----------------------------------------------------------------------------------------------
+
+
+def _shift_for(tilts, z, wavelength, du, oversample):
+    """Field.shift for an explicit tilt list (lentil/field.py:183-194, indexing='ij')."""
+    x, y = 0, 0
+    for t in tilts:
+        x, y = t.__shift__(xs=x, ys=y, z=z, wavelength=wavelength)
+    return -(y / du[1] * oversample), x / du[0] * oversample
+
+
+def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, oversample=2,
+                        mask=None, weights=None, tilts=None, out=None, chunk_bytes=8 << 30,
+                        distributed=False, return_device=False):
+    """Polychromatic, multi-field-point PSF stack in one call.
+
+    Equivalent to the reference user loop (docs/user/performance.rst:44-49)::
+
+        for p, tilt in enumerate(tilts):
+            for wl, wt in zip(wavelengths, weights):
+                w = Wavefront(wl, tilt=tilt) * plane
+                w = propagate_dft(w, pixelscale, shape, prop_shape, oversample, mask)
+                img[p] = w.insert(img[p], wt)
+
+    plane : Pupil (or Plane with ptype pupil/image and a focal length on the wavefront side)
+    wavelengths : (L,) metres;  weights : (L,) default 1
+    tilts : None (on-axis, returns (H, W)) or sequence of [rx, ry] field points (returns (P, H, W))
+    out : optional float64 device tensor to accumulate into (shape (P, H, W) or (H, W))
+    distributed : shard the wavelengths over torch.distributed ranks and all-reduce the stack
+    return_device : return the device tensor instead of a numpy array
+    """
+    from .plane import Tilt
+    wavelengths = np.asarray(wavelengths, dtype=float).reshape(-1)
+    L = len(wavelengths)
+    weights = np.ones(L) if weights is None else np.asarray(weights, dtype=float).reshape(-1)
+    if len(weights) != L:
+        raise ValueError('weights and wavelengths must have the same length')
+    squeeze = tilts is None
+    points = [None] if tilts is None else [Tilt(x=t[0], y=t[1]) for t in tilts]
+    P = len(points)
+
+    if plane.ptype not in (_pt.pupil, _pt.image):
+        raise TypeError("Wavefront must have ptype 'pupil' or 'image'")
+    ops = plane._operands()
+    if ops['scalar'] is not None:
+        raise ValueError('propagate_dft_batch needs a plane with array amplitude or opd')
+
+    shape = np.broadcast_to(shape, (2,))
+    prop_shape = np.asarray(shape) if prop_shape is None else np.broadcast_to(prop_shape, (2,))
+    shape_out = shape * oversample
+    prop_shape_out = prop_shape * oversample
+    out_extent = _output_extent(shape_out, mask)
+    H, W = int(shape_out[0]), int(shape_out[1])
+    dx = np.broadcast_to(plane.pixelscale, (2,))
+    du = np.broadcast_to(pixelscale, (2,))
+    z = getattr(plane, 'focal_length', None)
+
+    rank, world = 0, 1
+    if distributed:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+    my = np.arange(L)[rank::world] if world > 1 else np.arange(L)
+
+    stack = out if out is not None else device.zeros_f64(P, H, W)
+    stack3 = stack.view(P, H, W)
+
+    nseg = ops['nseg']
+    seg_tilts = [[plane.tilt[n]] if plane.tilt else [] for n in range(nseg)]
+    # bytes per wavelength: phasors + (transposed intermediate + output window) per field point
+    per_lam = 16 * ops['total'] + P * sum(
+        16 * (int(ops['segs'][n].w) * int(prop_shape_out[0]) + int(prop_shape_out[0]) * int(prop_shape_out[1]))
+        for n in range(nseg))
+    step = max(1, int(chunk_bytes // max(per_lam, 1)))
+
+    for c0 in range(0, len(my), step):
+        idx = my[c0:c0 + step]
+        lam = wavelengths[idx]
+        _, phasors = plane._phasors(lam)                                   # K1
+        jobs = []       # (l, p, n, plan)
+        for li, wl in enumerate(lam):
+            for p, pt in enumerate(points):
+                for n in range(nseg):
+                    tl = ([pt] if pt is not None else []) + seg_tilts[n]
+                    plan = plan_window(_shift_for(tl, z, wl, du, oversample), prop_shape_out, out_extent)
+                    if plan is not None:
+                        jobs.append((li, p, n, plan))
+        if not jobs:
+            continue
+        total = sum(int(j[3][0][0]) * int(j[3][0][1]) for j in jobs)
+        buf = device.empty_c128(total)
+        descs = (_lib.MftDesc * len(jobs))()
+        fields_by_point = [[] for _ in range(P)]
+        pos = 0
+        for k, (li, p, n, (ishape, ishift, dshift)) in enumerate(jobs):
+            h, w = int(ishape[0]), int(ishape[1])
+            win = buf[pos:pos + h * w].view(h, w)
+            pos += h * w
+            alpha = _dft_alpha(dx=dx, du=du, z=z, wavelength=lam[li], oversample=oversample)
+            _fourier.mft_descriptor(descs[k], plane._segment_view(ops, phasors[li], n), win, alpha,
+                                    dshift, ops['offsets'][n], unitary=True)
+            fields_by_point[p].append((li, Field(win, offset=ishift)))
+        _fourier.run_mft(descs, len(jobs))                                 # K2a
+        for p in range(P):                                                 # K3
+            fl = fields_by_point[p]
+            if fl:
+                _field.accumulate_intensity([f for _, f in fl], stack3[p], [li for li, _ in fl],
+                                            [float(weights[idx[li]]) for li, _ in fl])
+
+    if distributed and world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(stack, op=dist.ReduceOp.SUM)
+    result = stack3[0] if squeeze else stack3
+    return result if return_device else device.to_host(result)

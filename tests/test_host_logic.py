@@ -1,0 +1,231 @@
+"""Host-side mirror of the reference interface (integer geometry, metadata, error behaviour)
+and the C-ABI export table.  CPU only: nothing here launches a kernel."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import lentil_b200 as lentil
+import lentil_oracle as oc
+from lentil_b200 import _lib, extent, helper
+from lentil_b200.propagate import plan_window, _mask_shape, _mask_shift
+from conftest import ROOT
+
+
+# ---- C ABI ------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "lentil_b200.h")).read()
+    declared = set(re.findall(r"\b(lfd_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(handle, name), f"{name} declared in include/lentil_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def test_struct_layouts_match():
+    L = _lib.lib()
+    assert L.lfd_abi_version() == 1
+    assert L.lfd_struct_size(0) == ctypes.sizeof(_lib.MftDesc)
+    assert L.lfd_struct_size(1) == ctypes.sizeof(_lib.Segment)
+    assert L.lfd_struct_size(2) == ctypes.sizeof(_lib.Window)
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    L = _lib.lib()
+    d = (_lib.MftDesc * 1)()
+    assert L.lfd_mft_c128_batched(d, 1, None, 0, None) != 0
+    assert b"workspace" in L.lfd_last_error()
+    assert L.lfd_mft_c128_batched(d, 0, None, 0, None) == 0      # empty batch is a no-op
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError):
+        lentil.fourier.dft2(np.ones((4, 4)), 0.25)
+
+
+# ---- extent / helper: bit-exact integer logic -----------------------------------------------------
+def test_extent_matches_golden(golden):
+    for row in golden("extent")["rows"]:
+        sa, sb, ha, hb = tuple(row[0:2]), tuple(row[2:4]), tuple(row[4:6]), tuple(row[6:8])
+        ea, eb = tuple(row[8:12]), tuple(row[12:16])
+        assert extent.array_extent(sa, ha) == ea and extent.array_extent(sb, hb) == eb
+        assert extent.intersect(ea, eb) == bool(row[16])
+        ishape = extent.intersection_shape(ea, eb)
+        assert (tuple(ishape) if ishape else (0, 0)) == tuple(row[17:19])
+        assert extent.intersection_shift(ea, eb) == tuple(row[19:21])
+        assert extent.intersection_slices(ea, eb) == oc.intersection_slices(ea, eb)
+        assert extent.array_center(ea) == oc.array_center(ea)
+
+
+def test_extent_float_shift_truncates_toward_zero():
+    # lentil/extent.py:28-29 uses int(); callers pass np.fix'd shifts
+    for s in (-2.7, -0.2, 0.9, 3.999):
+        assert extent.array_extent((5, 4), (s, -s)) == oc.array_extent((5, 4), (s, -s))
+    assert extent.array_extent((), (3, -2)) == oc.array_extent((), (3, -2)) == (3, 3, -2, -2)
+
+
+def test_helper_matches_golden(golden):
+    d = golden("helper")
+    for i in range(int(d["nh"])):
+        a = d[f"h{i}_a"]
+        slc = helper.boundary_slice(a)
+        assert [slc[0].start, slc[0].stop, slc[1].start, slc[1].stop] == list(d[f"h{i}_slice"])
+        assert tuple(helper.slice_offset(slc, a.shape)) == tuple(d[f"h{i}_offset"])
+    assert helper.slice_offset(Ellipsis, (4, 4)) == (0, 0)
+
+
+def test_boundary_slice_random():
+    # reference tests/test_helper.py:14-26
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        a = np.zeros((10, 10))
+        r, c = rng.integers(0, 10, 2)
+        a[r:r + 3, c:c + 3] = 1
+        assert helper.boundary_slice(a) == (slice(r, min(r + 3, 10)), slice(c, min(c + 3, 10)))
+
+
+def test_plan_window_matches_oracle_on_random_shifts():
+    rng = np.random.default_rng(11)
+    n_hit = 0
+    for _ in range(500):
+        shape_out = tuple(int(v) for v in rng.integers(8, 200, 2))
+        prop = tuple(int(v) for v in np.minimum(rng.integers(4, 200, 2), shape_out))
+        shift = rng.uniform(-150, 150, 2)
+        if rng.random() < 0.3:
+            mshape = tuple(int(v) for v in rng.integers(1, min(shape_out) + 1, 2))
+            mshift = tuple(int(v) for v in rng.integers(-20, 20, 2))
+            oe = extent.array_extent(mshape, mshift)
+        else:
+            oe = extent.array_extent(shape_out, (0, 0))
+        a, b = plan_window(shift, prop, oe), oc.plan_window(shift, prop, oe)
+        if b is None:
+            assert a is None
+            continue
+        n_hit += 1
+        assert tuple(a[0]) == tuple(b[0]) and tuple(a[1]) == tuple(b[1])
+        assert np.array_equal(a[2], b[2])
+    assert n_hit > 100
+
+
+def test_plan_window_worked_example():
+    # SURVEY.md appendix A.3
+    out_extent = extent.array_extent((512, 512), (0, 0))
+    ishape, ishift, dshift = plan_window((26.4, 13.6), (512, 512), out_extent)
+    assert tuple(ishape) == (486, 499) and tuple(ishift) == (13, 6)
+    assert np.allclose(dshift, (13.4, 7.6))
+
+
+def test_mask_window_matches_oracle():
+    rng = np.random.default_rng(2)
+    for _ in range(20):
+        m = np.zeros((40, 50))
+        r, c = rng.integers(0, 30, 2)
+        h, w = rng.integers(1, 10, 2)
+        m[r:r + h, c:c + w] = rng.random((min(h, 40 - r), min(w, 50 - c))) + 0.1
+        shape, shift = oc.mask_window(m)
+        assert tuple(_mask_shape(m)) == tuple(shape) and tuple(_mask_shift(m)) == tuple(shift)
+
+
+# ---- metadata objects ----------------------------------------------------------------------------
+def test_ptype():
+    assert lentil.ptype(None) == lentil.none and lentil.ptype('pupil') == lentil.pupil
+    assert hash(lentil.ptype('image')) == hash(lentil.image) and str(lentil.tilt) == 'tilt'
+    with pytest.raises(TypeError):
+        lentil.ptype('bogus')
+
+
+def test_default_wavefront():
+    # reference tests/test_wavefront.py:6-14
+    w = lentil.Wavefront(wavelength=500e-9)
+    assert np.array_equal(w.field, 1 + 0j)
+    assert np.array_equal(w.intensity, 1)
+    assert lentil.Plane() * w
+
+
+def test_propagate_requires_pupil_or_image():
+    # reference tests/test_wavefront.py:16-19
+    w = lentil.Wavefront(wavelength=500e-9)
+    with pytest.raises(TypeError):
+        lentil.propagate_dft(w, shape=(64, 64), pixelscale=5e-6)
+
+
+def test_wavefront_ptype_guard_and_tilt_arg():
+    with pytest.raises(TypeError):
+        lentil.Wavefront(500e-9, ptype='tilt')
+    with pytest.raises(ValueError):
+        lentil.Wavefront(500e-9, tilt=[1, 2, 3])
+    w = lentil.Wavefront(500e-9, tilt=[3e-6, -2e-6])
+    t = w.data[0].tilt[0]
+    assert (t.x, t.y) == (-2e-6, 3e-6)          # constructor swap, lentil/plane.py:898-901
+    assert t.__shift__(xs=1.0, ys=2.0, z=10.0) == (1.0 + 2e-5, 2.0 - 3e-5)
+
+
+def test_field_shift_matches_oracle():
+    rng = np.random.default_rng(4)
+    for _ in range(20):
+        tl = rng.normal(size=(3, 2)) * 1e-5
+        f = lentil.Field(1, tilt=[lentil.Tilt(x=a, y=b) for a, b in tl])
+        g = oc.make_field(1, None, [oc.tilt_entry(a, b) for a, b in tl])
+        a = f.shift(z=17.0, wavelength=6e-7, pixelscale=(5e-6, 4e-6), oversample=3)
+        assert a == oc.field_shift(g, 17.0, (5e-6, 4e-6), 3)
+
+
+@pytest.mark.parametrize('field_shape, field_shift, output_shape', [
+    ((5, 5), (-25, 0), (10, 10)), ((5, 5), (25, 0), (10, 10)),
+    ((5, 5), (0, -25), (10, 10)), ((5, 5), (0, 25), (10, 10))])
+def test_overlap(field_shape, field_shift, output_shape):
+    # reference tests/test_wavefront.py:22-29
+    assert lentil.wavefront._overlap(field_shape, field_shift, output_shape) is False
+
+
+def test_scalar_field_products():
+    # the scalar rows of reference tests/test_field.py:7-27 (array rows run on the GPU)
+    F = lentil.Field
+    c = F(1, pixelscale=1, offset=[0, 0]) * F(1, pixelscale=1, offset=[0, 0])
+    assert np.array_equal(c.data, 1 + 0j) and np.array_equal(c.offset, [0, 0])
+    assert (F(1, pixelscale=1, offset=[0, 0]) * F(1, pixelscale=1, offset=[1, 0])).size == 0
+    assert (F(1, pixelscale=1, offset=[0, 0]) * F(1, pixelscale=1, offset=[-10, 0])).size == 0
+
+
+def test_mul_ptype_rules_and_pixelscale():
+    w = lentil.Wavefront(500e-9, ptype='image')
+    with pytest.raises(TypeError):
+        lentil.Pupil() * w                       # image wavefront x pupil plane is not allowed
+    with pytest.raises(ValueError):
+        lentil.Plane(pixelscale=1.0) * lentil.Wavefront(500e-9, pixelscale=2.0)
+    out = lentil.Tilt(1e-6, 2e-6) * lentil.Wavefront(500e-9)
+    assert len(out.data) == 1 and len(out.data[0].tilt) == 1
+
+
+def test_freeze_semantics():
+    p = lentil.Plane(amplitude=np.ones((4, 4)), opd=np.zeros((4, 4)))
+    p.freeze()
+    with pytest.raises(RuntimeError):
+        p.opd = np.ones((4, 4))
+    with pytest.raises(RuntimeError):
+        p.freeze()
+    p.thaw()
+    p.opd = np.ones((4, 4))
+    assert p.size == 1 and p.shape == (4, 4)
+
+
+def test_fit_tilt_recovers_a_plane():
+    rng = np.random.default_rng(8)
+    n, dx = 48, 1 / 40
+    from lentil_b200 import synth
+    amp = synth.circle((n, n), 18)
+    rr, cc = helper.mesh((n, n))
+    opd = (2e-7 + 3e-6 * rr * dx - 1.5e-6 * (-cc) * dx) * amp
+    p = lentil.Pupil(amplitude=amp, opd=opd, pixelscale=dx, focal_length=5.0)
+    q = p.fit_tilt(inplace=False)
+    assert q is not p and len(p.tilt) == 0 and len(q.tilt) == 1
+    assert np.allclose(q.opd[amp > 0], 2e-7, atol=1e-15)
+    assert np.isclose(q.tilt[0].y, 3e-6) and np.isclose(q.tilt[0].x, -1.5e-6)
+    assert p.fit_tilt(inplace=True) is p
+    assert lentil.Image(amplitude=amp).fit_tilt() is not None
