@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py — PSF planes/s on the BASELINE.json headline workload.
+
+Workload (BASELINE.json configs[1]): polychromatic obscured-aperture PSF — 1024^2 annular pupil
+(bbox 1001^2) with Zernike WFE, 100 wavelengths 500-900 nm, 512^2 detector at oversample 2
+(1024^2 samples).  One *plane* = one dft2 (one Field at one wavelength); one *step* = one pass of
+the hot path over the 100-wavelength batch: K1 pupil prep -> K2a matrix Fourier transform
+(FP64 DMMA) -> K3 |E|^2 accumulate.  With N ranks every rank takes 100 wavelengths of a 100*N
+wavelength PSF (weak scaling) and the local PSFs are summed with one NCCL all-reduce per step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM, CUDA-event time, max over ranks.
+`e2e`: the public API with host (pinned) numpy arrays in and a numpy PSF out, copies inside the
+timed region.  `roofline`: the MFT kernel against the FP64 tensor (DMMA) issue rate.
+`cpu_baseline` / `--impl reference`: the reference algorithm (oracle port, numpy + BLAS) on the
+host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(n=1024, radius=500, obscuration=1 / 3, nzern=15, nlam=100, lam0=500e-9, lam1=900e-9,
+                det=512, oversample=2, dx=1 / 1000, z=20.0, du=5e-6)
+
+
+def make_inputs(nlam):
+    from lentil_b200 import synth
+    w = WORKLOAD
+    mask = synth.annulus((w["n"], w["n"]), w["radius"], w["obscuration"])
+    amp = synth.normalize_power(mask)
+    opd = synth.zernike_opd(mask, np.random.default_rng(0).normal(size=w["nzern"]) * 30e-9)
+    wls = np.linspace(w["lam0"], w["lam1"], nlam)
+    wts = np.full(nlam, 1.0 / nlam)
+    return amp, opd, wls, wts
+
+
+def plane_flops(m, n, M, N):
+    """8*M*n*(m+N) real flops per plane (complex MAC = 8)."""
+    return 8.0 * M * n * (m + N)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_psf(amp, opd, wls, wts):
+    """The reference algorithm on the host: the real lentil if an install is present under
+    baseline/_ref (driver-provided), else the oracle port (numpy + BLAS, same arithmetic)."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    w = WORKLOAD
+    if os.path.isdir(os.path.join(ref_dir, "lentil")):
+        sys.path.insert(0, ref_dir)
+        import lentil
+        p = lentil.Pupil(amplitude=amp, opd=opd, pixelscale=w["dx"], focal_length=w["z"])
+        img = np.zeros((w["det"] * w["oversample"],) * 2)
+        for wl, wt in zip(wls, wts):
+            wf = lentil.propagate_dft(lentil.Wavefront(wl) * p, pixelscale=w["du"], shape=(w["det"],) * 2,
+                                      oversample=w["oversample"])
+            img = wf.insert(img, wt)
+        return img, "reference"
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lentil_oracle as oc
+    img = oc.psf(amp, opd, None, wls, wts, (w["dx"], w["dx"]), w["z"], w["du"], (w["det"],) * 2, None,
+                 w["oversample"])
+    return img, "port"
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [i.get("num_threads", 1) for i in threadpool_info() if i.get("user_api") == "blas"]
+        return max(n) if n else 1
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def time_cpu(amp, opd, wls, wts, budget_s, max_planes):
+    """Planes/s of the CPU reference on a bounded sample: wavelengths taken evenly from the
+    workload until `budget_s` seconds or `max_planes` are spent (first plane = warm-up)."""
+    pick = np.linspace(0, len(wls) - 1, max_planes).round().astype(int)
+    cpu_reference_psf(amp, opd, wls[pick[:1]], wts[pick[:1]])           # BLAS thread spin-up
+    done, t0, kind = 0, time.perf_counter(), "port"
+    for k in pick:
+        _, kind = cpu_reference_psf(amp, opd, wls[k:k + 1], wts[k:k + 1])
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, done, dt, kind
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    amp, opd, wls, wts = make_inputs(WORKLOAD["nlam"])
+    per_step = 4
+    cpu_reference_psf(amp, opd, wls[:1], wts[:1])
+    for _ in range(args.warmup):
+        cpu_reference_psf(amp, opd, wls[:1], wts[:1])
+    pick = np.linspace(0, len(wls) - 1, per_step * max(args.steps, 1)).round().astype(int)
+    t0 = time.perf_counter()
+    kind = "port"
+    for s in range(args.steps):
+        idx = pick[s * per_step:(s + 1) * per_step]
+        _, kind = cpu_reference_psf(amp, opd, wls[idx], wts[idx])
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    cores = blas_threads()
+    sample = (f"{per_step} of the {WORKLOAD['nlam']} wavelengths per step (evenly spaced), full "
+              f"Wavefront*Pupil -> propagate_dft -> insert per wavelength")
+    print(json.dumps({
+        "impl": "reference", "metric": "psf_planes_per_sec", "value": value, "unit": "planes/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "planes/s", "cores": cores, "kind": kind, "sample": sample,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": "planes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(n_gpus):
+    w = WORKLOAD
+    return {"workload": "BASELINE configs[1]: polychromatic obscured-aperture PSF, 1024^2 annular pupil "
+                        "(bbox 1001^2) + 15 Zernike WFE -> 512^2 detector x oversample 2 (1024^2 samples), "
+                        f"{w['nlam']} wavelengths 500-900 nm per GPU",
+            "plane": "1001x1001 -> 1024x1024 complex128", "planes_per_step_per_gpu": w["nlam"],
+            "gflop_per_plane": plane_flops(1001, 1001, 1024, 1024) / 1e9,
+            "parallelism": f"wavelength-sharded x{n_gpus}, NCCL all-reduce of the PSF per step" if n_gpus > 1
+            else "single GPU",
+            "l2": "per-step working set ~4.9 GB (phasors + intermediates + fields) >> 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import lentil_b200 as lentil
+    from lentil_b200 import device, fourier
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = device.set_device(local)
+    w = WORKLOAD
+    nlam_total = w["nlam"] * world
+    amp, opd, wls, wts = make_inputs(nlam_total)
+    shape = (w["det"], w["det"])
+
+    pupil = lentil.Pupil(amplitude=amp, opd=opd, pixelscale=w["dx"], focal_length=w["z"])
+    pupil.freeze()                                         # operands resident in HBM
+
+    def step_resident():
+        return lentil.propagate_dft_batch(pupil, wls, w["du"], shape, oversample=w["oversample"], weights=wts,
+                                          distributed=world > 1, return_device=True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up -------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        psf = step_resident()
+    barrier()
+
+    # ---- timed: resident inputs, device time, with the MFT kernel timed on its own ------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    fourier.TIMERS = []
+    launches0 = device.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        psf = step_resident()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = device.launch_count() - launches0
+    mft_ms = sum(a.elapsed_time(b) for a, b, _ in fourier.TIMERS)
+    mft_flops = sum(f for _, _, f in fourier.TIMERS)
+    mft_launches = 2 * len(fourier.TIMERS)
+    fourier.TIMERS = None
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms, mft_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, mft_ms = float(t[0]), float(t[1])
+    planes = w["nlam"] * world * args.steps
+    value = planes / (ms * 1e-3)
+
+    # ---- e2e: public API, host arrays in (pinned), numpy PSF out, copies inside the timed region ---
+    amp_pin = torch.from_numpy(amp).pin_memory()
+    opd_pin = torch.from_numpy(opd).pin_memory()
+    amp_h, opd_h = amp_pin.numpy(), opd_pin.numpy()
+
+    def step_e2e():
+        p = lentil.Pupil(amplitude=amp_h, opd=opd_h, pixelscale=w["dx"], focal_length=w["z"])
+        return lentil.propagate_dft_batch(p, wls, w["du"], shape, oversample=w["oversample"], weights=wts,
+                                          distributed=world > 1)
+
+    out = step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = planes / float(t[0])
+    h2d = amp.nbytes + opd.nbytes + amp.size          # amplitude, opd, uint8 mask
+    d2h = out.nbytes
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------
+    probe = device.probe_fp64()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    achieved = mft_flops / (mft_ms * 1e-3) / 1e12 if mft_ms > 0 else None
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "mft_ncu_summary.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {
+        "bound": "tensor", "kernel": "mft_stage_kernel (K2a, FP64 DMMA.8x8x4)",
+        "achieved": achieved, "peak": probe["dmma_tflops"], "unit": "TFLOP/s",
+        "frac": achieved / probe["dmma_tflops"] if achieved else None,
+        "traffic": traffic,
+        "peak_source": "measured in this run by lfd_probe_fp64 (register-resident DMMA.8x8x4 issue loop, all SMs); "
+                       "MEASURED_PEAKS.json carries HBM and bf16 only (hbm_gbs=%s, bf16_tflops=%s); nominal FP64 "
+                       "tensor = 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2 TFLOP/s"
+                       % (peaks.get("hbm_gbs"), peaks.get("bf16_tflops")),
+        "flops_per_launch": mft_flops / max(mft_launches, 1),
+        "avg_launch_ms": mft_ms / max(mft_launches, 1), "launches": mft_launches,
+        "share_of_step": mft_ms / ms,
+    }
+
+    # ---- CPU baseline (bounded sample of the same workload) -------------------------------------------
+    cpu_value, cpu_planes, cpu_s, kind = time_cpu(amp, opd, wls[:w["nlam"]], wts[:w["nlam"]], budget_s=12.0,
+                                                  max_planes=40)
+    # parity spot check of this very run against the CPU reference (one wavelength)
+    ref1, _ = cpu_reference_psf(amp, opd, wls[:1], wts[:1])
+    got1 = lentil.propagate_dft_batch(pupil, wls[:1], w["du"], shape, oversample=w["oversample"], weights=wts[:1])
+    parity = float(np.max(np.abs(got1 - ref1)) / np.max(ref1))
+
+    line = {
+        "metric": "psf_planes_per_sec", "value": value, "unit": "planes/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(world),
+        "tflops_algorithmic": value * plane_flops(1001, 1001, 1024, 1024) / 1e12,
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": "planes/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "api": "lentil_b200.propagate_dft_batch(Pupil(numpy...)) -> numpy"},
+        "roofline": roofline,
+        "cpu_baseline": {"value": cpu_value, "unit": "planes/s", "cores": blas_threads(), "kind": kind,
+                         "host_cpus": os.cpu_count(),
+                         "sample": f"{cpu_planes} of the {w['nlam']} wavelengths (evenly spaced) in {cpu_s:.1f} s, "
+                                   "full Wavefront*Pupil -> propagate_dft -> insert per wavelength"},
+        "parity_peak_normalised_error": parity,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -32,13 +32,29 @@ def mft_descriptor(desc, f_dev, out_dev, alpha, shift, offset, unitary=True, inv
     return desc
 
 
+# bench.py sets this to a list to get (start event, end event, algorithmic flops) per batched launch
+TIMERS = None
+
+
+def mft_flops(descs, count):
+    """Algorithmic flops of a batch, 8*M*n*(m+N) per plane."""
+    return float(sum(8.0 * d.M * d.n * (d.m + d.N) for d in descs[:count]))
+
+
 def run_mft(descs, count):
     """Launch a batch of planes on the current stream with a torch-owned workspace."""
     L = _lib.lib()
     need = L.lfd_mft_workspace_bytes(descs, count)
     ws = device.empty_bytes(need)
+    if TIMERS is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.check(L.lfd_mft_c128_batched(descs, count, ws.data_ptr(), need, device.stream_ptr()),
                "lfd_mft_c128_batched")
+    if TIMERS is not None:
+        e1.record()
+        TIMERS.append((e0, e1, mft_flops(descs, count)))
     return ws
 
 
