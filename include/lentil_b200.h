@@ -60,6 +60,15 @@ typedef struct lfd_mft_desc {
     int32_t     inverse;            /* 0: dft2, 1: idft2 semantics                     */
 } lfd_mft_desc;
 
+/* Two executions of the same transform (results agree to rounding):
+ *   LFD_MFT_DIRECT : complex twiddle x complex data, 4 real DMMAs per complex 8x8x4 block
+ *   LFD_MFT_FOLDED : even/odd folding of both axes -> real twiddles, 4x fewer DMMAs (default)
+ * Process-wide switch; affects lfd_mft_workspace_bytes and the lfd_mft_* launches that follow. */
+#define LFD_MFT_DIRECT 0
+#define LFD_MFT_FOLDED 1
+int lfd_set_mft_variant(int variant);
+int lfd_get_mft_variant(void);
+
 /* bytes of device workspace lfd_mft_c128_batched needs for `count` planes whose largest
  * intermediate is max over planes of (n * M) complex elements */
 size_t lfd_mft_workspace_bytes(const lfd_mft_desc *descs_host, int count);

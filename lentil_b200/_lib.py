@@ -53,6 +53,8 @@ SIGNATURES = {
     "lfd_launch_count": (C.c_uint64, []),
     "lfd_struct_size": (C.c_size_t, [C.c_int]),
     "lfd_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
+    "lfd_set_mft_variant": (C.c_int, [C.c_int]),
+    "lfd_get_mft_variant": (C.c_int, []),
     "lfd_mft_workspace_bytes": (C.c_size_t, [C.POINTER(MftDesc), C.c_int]),
     "lfd_mft_c128_batched": (C.c_int, [C.POINTER(MftDesc), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "lfd_mft_c128": (C.c_int, [C.POINTER(MftDesc), C.c_void_p, C.c_size_t, C.c_void_p]),

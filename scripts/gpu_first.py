@@ -37,6 +37,9 @@ def main():
     _lib.check(L.lfd_probe_fp64(out, 20000), "probe")
     print(json.dumps({"probe_dmma_tflops": out[0], "probe_dfma_tflops": out[1], "clock_mhz": out[2]}))
 
+    variant = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+    L.lfd_set_mft_variant(variant)
+    print("variant", L.lfd_get_mft_variant())
     ctx = L.lfd_ctx_create(0)
     assert ctx, L.lfd_last_error()
     rng = np.random.default_rng(0)

@@ -11,7 +11,7 @@ import lentil_oracle as oc
 from lentil_b200 import _lib
 from conftest import peak_err, TOL64
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures('mft_variant')]
 
 
 def test_golden_vectors(golden):

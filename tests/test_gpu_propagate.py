@@ -9,7 +9,7 @@ import lentil_oracle as oc
 from lentil_b200 import synth
 from conftest import peak_err, unpack_fields, TOL64
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures('mft_variant')]
 
 
 def _check_fields(wavefront, gold, tol=TOL64):
