@@ -8,8 +8,8 @@
 //     (R+o)(U-s) = R'U' - s'R' + o'(U'-s'),        o' = o - cR,  s' = s + cU
 //
 //     exp(sgn 2 pi i a (R+o)(U-s)) = [cos th + i sgn sin th] * pre(R') * post(U'),   th = 2 pi a R'U'
-//     pre(R')  = exp(-sgn 2 pi i a s' R')      (a phase ramp on the input rows:  fold kernel)
-//     post(U') = exp( sgn 2 pi i a o'(U'-s'))  (a phase ramp on the output rows: MFT epilogue)
+//     pre(R')  = exp(-sgn 2 pi i a s' R')      (a phase ramp on the input rows)
+//     post(U') = exp( sgn 2 pi i a o'(U'-s'))  (a phase ramp on the output rows)
 //
 // cos th is even and sin th odd in both R' and U', so with g = pre * f folded into
 //     ge[r] = g[+R'_r] + g[-R'_r],   go[r] = g[+R'_r] - g[-R'_r]            (r = 0 .. ceil(K/2)-1)
@@ -21,52 +21,63 @@
 // stage instead of 4*M*K*n.  Exact in exact arithmetic, for any alpha / shift / offset / parity;
 // rounding differs from the direct form by a few ulp (parity gate 1e-10, observed ~1e-14).
 //
-// Kernel structure is that of mft_c128.cu: cos/sin A-fragments live in registers and advance by
-// a per-row rotation each DMMA k-step, ge/go tiles are staged with cp.async, the product is
-// stored transposed so that the next stage again sees "K x C, C contiguous".
+// Launch sequence for a batch:   fold_kernel (f -> ge1/go1)
+//                                mft_folded_kernel<true>   rows:    ge1/go1 -> ge2/go2
+//                                mft_folded_kernel<false>  columns: ge2/go2 -> F
+// The row stage writes its result ALREADY FOLDED for the column stage: a CTA owns 16 folded column
+// indices = 16 columns and their 16 mirror images, laid out in shared memory so that a lane's
+// accumulators hold T[., j+] and T[., j-] side by side; its epilogue forms pre*T+ +- conj(pre)*T-
+// and stores them transposed.  The intermediate T never exists in HBM.
+//
+// Kernel structure otherwise follows mft_c128.cu: cos/sin A-fragments live in registers and
+// advance by a per-row rotation each DMMA k-step; ge/go tiles are staged with cp.async.
 #include "lfd_common.cuh"
 
 namespace lfd {
 
-constexpr int FBR = 128;     // folded output rows per CTA
+constexpr int FBR = 64;      // folded output rows per CTA
 constexpr int FBC = 32;      // complex data columns per CTA
 constexpr int FBK = 16;      // folded K rows per smem stage
 constexpr int FSTAGES = 4;
 constexpr int FLDS = FBC + 2;  // complex elements per smem row: LDS.128 conflict-free (see mft_c128.cu)
-constexpr int FTHREADS = 256;
-constexpr int FWARPS_C = 2;  // 4 x 2 warps, each 32 folded rows x 16 complex columns
-constexpr int FRESEED_TILES = 16;
+constexpr int FTHREADS = 128;  // 4 warps stacked along the rows, each 16 folded rows x 32 complex columns
+                               // (a twiddle element feeds 8 DMMAs); two CTAs per SM so that one CTA's
+                               // prologue / epilogue hides under the other's MMAs
+constexpr int FRESEED_TILES = 64;  // re-seed the twiddle recurrence every 1024 folded K (2048 input rows)
 constexpr size_t FSMEM_BYTES = (size_t)FSTAGES * 2 * FBK * FLDS * sizeof(double2);
 
 struct FoldDesc {
     const double2 *D;   // K x C
     long long ldd;
     double2 *G;         // ge plane (Kf x C, ld = C) followed by go plane
-    int K, C, Kf, hm, cR2;
-    int row_base;
+    int K, C, Kf, hm, cR2, pad_;
     double alpha, sprime, sgn;
 };
 
 struct FStageDesc {
-    const double2 *G;   // ge at G, go at G + Kf*C
-    double2 *O;
+    const double2 *G;   // ge at G, go at G + Kf*C   (Kf x C each, ld = C)
+    double2 *O;         // FOLD_OUT: ge/go planes of the next stage (nKf x nldg each); else out (ld = ldo)
     long long ldo;
     int Kf, C, Rf, M, hM, cR2, cU2;
-    int tiles_r, tiles_c, tile_base;
+    int tiles_r, tiles_c;
+    int nKf, nhm, ncR2;           // FOLD_OUT: folding of the data columns for the next stage
+    long long nldg;
     double alpha, oprime, sprime, scale, sgn;
+    double nalpha, nsprime;
 };
+
+// z = x * y (complex)
+__device__ __forceinline__ void cmul(double xr, double xi, double yr, double yi, double &zr, double &zi) {
+    zr = xr * yr - xi * yi;
+    zi = xr * yi + xi * yr;
+}
 
 // ---- fold: g = pre * f, ge/go = g[+R'] +- g[-R'] -------------------------------------------------
 __global__ void __launch_bounds__(256)
-fold_kernel(const FoldDesc *__restrict__ descs, int count) {
-    int row = blockIdx.x;
-    int lo = 0, hi = count - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (descs[mid].row_base <= row) lo = mid; else hi = mid - 1;
-    }
-    const FoldDesc d = descs[lo];
-    const int r = row - d.row_base;
+fold_kernel(const FoldDesc *__restrict__ descs) {
+    const FoldDesc d = descs[blockIdx.y];
+    const int r = blockIdx.x;
+    if (r >= d.Kf) return;
     const double Rp = (double)r + 0.5 * d.cR2;
     __shared__ double pre[2];
     if (threadIdx.x == 0) {
@@ -100,6 +111,9 @@ fold_kernel(const FoldDesc *__restrict__ descs, int count) {
 }
 
 // ---- folded MFT stage ---------------------------------------------------------------------------
+// FOLD_OUT: smem columns 0..15 hold data columns j+ = nhm + r2, columns 16..31 their mirrors
+// j- = nhm - r2 - ncR2, for the 16 folded column indices r2 = cf_base .. cf_base+15.
+template <bool FOLD_OUT>
 __device__ __forceinline__ void f_load_tile(double2 *sd, const FStageDesc &d, int k_base, int c_base,
                                             int tid) {
 #pragma unroll
@@ -107,59 +121,67 @@ __device__ __forceinline__ void f_load_tile(double2 *sd, const FStageDesc &d, in
         int idx = tid + i * FTHREADS;
         int p = idx / (FBK * FBC), rem = idx % (FBK * FBC);
         int kk = rem / FBC, cc = rem % FBC;
-        int gk = k_base + kk, gc = c_base + cc;
-        bool ok = (gk < d.Kf) && (gc < d.C);
+        int gk = k_base + kk, gc;
+        bool ok = gk < d.Kf;
+        if (FOLD_OUT) {
+            int r2 = c_base + (cc & 15);
+            gc = (cc < 16) ? (d.nhm + r2) : (d.nhm - r2 - d.ncR2);
+            ok = ok && (r2 < d.nKf) && (gc >= 0) && (gc < d.C);
+        } else {
+            gc = c_base + cc;
+            ok = ok && (gc < d.C);
+        }
         const double2 *src = ok ? (d.G + ((long long)p * d.Kf + gk) * d.C + gc) : d.G;
         cp_async16(sd + (p * FBK + kk) * FLDS + cc, src, ok);
     }
 }
 
-__global__ void __launch_bounds__(FTHREADS, 1)
-mft_folded_kernel(const FStageDesc *__restrict__ descs, int count) {
+template <bool FOLD_OUT>
+__global__ void __launch_bounds__(FTHREADS, 2)
+mft_folded_kernel(const FStageDesc *__restrict__ descs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2 *sD = reinterpret_cast<double2 *>(smem_raw);
     constexpr int STAGE_ELEMS = 2 * FBK * FLDS;
 
-    int tile = blockIdx.x;
-    int lo = 0, hi = count - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (descs[mid].tile_base <= tile) lo = mid; else hi = mid - 1;
-    }
-    const FStageDesc d = descs[lo];
-    tile -= d.tile_base;
+    const FStageDesc d = descs[blockIdx.y];
+    const int tile = blockIdx.x;
+    if (tile >= d.tiles_r * d.tiles_c) return;
     const int tr = tile % d.tiles_r, tc = tile / d.tiles_r;
-    const int r_base = tr * FBR, c_base = tc * FBC;
+    const int r_base = tr * FBR;
+    const int c_base = FOLD_OUT ? tc * (FBC / 2) : tc * FBC;   // FOLD_OUT: base of the folded column index
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int wr = warp / FWARPS_C, wc = warp % FWARPS_C;
     const int KT = (d.Kf + FBK - 1) / FBK;
 
 #pragma unroll
     for (int s = 0; s < FSTAGES - 1; ++s) {
-        if (s < KT) f_load_tile(sD + s * STAGE_ELEMS, d, s * FBK, c_base, tid);
+        if (s < KT) f_load_tile<FOLD_OUT>(sD + s * STAGE_ELEMS, d, s * FBK, c_base, tid);
         cp_async_commit();
     }
 
     // accA[mb][q][part]: A = cos-GEMM on ge; accB: B = sin-GEMM on go.  part 0 = Re columns, 1 = Im.
-    double accA[4][2][2][2], accB[4][2][2][2];
+    double accA[2][4][2][2], accB[2][4][2][2];
 #pragma unroll
-    for (int mb = 0; mb < 4; ++mb)
+    for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
+        for (int q = 0; q < 4; ++q)
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
                 accA[mb][q][p][0] = accA[mb][q][p][1] = 0.0;
                 accB[mb][q][p][0] = accB[mb][q][p][1] = 0.0;
             }
 
-    double tc_[4], ts_[4], rc_[4], rs_[4], up[4];
+    // twiddle state (cos, sin) of this lane's A-fragment slots and the per-row rotation for K += 4.
+    // The lane's second row block is 8 rows below the first: one extra complex multiply, not a sincospi.
+    double tc_[2], ts_[2], rc_[2], rs_[2];
     const double cR = 0.5 * d.cR2, cU = 0.5 * d.cU2;
-#pragma unroll
-    for (int mb = 0; mb < 4; ++mb) {
-        up[mb] = (double)(r_base + wr * 32 + mb * 8 + g) + cU;          // U' of this lane's row
-        cis_cycles(d.alpha, 4.0, up[mb], 1.0, rc_[mb], rs_[mb]);
+    const double up0 = (double)(r_base + warp * 16 + g) + cU;            // U' of this lane's first row
+    {
+        double sc, ss;
+        cis_cycles(d.alpha, 4.0, up0, 1.0, rc_[0], rs_[0]);
+        cis_cycles(d.alpha, 4.0, 8.0, 1.0, sc, ss);
+        cmul(rc_[0], rs_[0], sc, ss, rc_[1], rs_[1]);
     }
 
     for (int kt = 0; kt < KT; ++kt) {
@@ -167,92 +189,155 @@ mft_folded_kernel(const FStageDesc *__restrict__ descs, int count) {
         __syncthreads();
         {
             int nk = kt + FSTAGES - 1;
-            if (nk < KT) f_load_tile(sD + (nk % FSTAGES) * STAGE_ELEMS, d, nk * FBK, c_base, tid);
+            if (nk < KT) f_load_tile<FOLD_OUT>(sD + (nk % FSTAGES) * STAGE_ELEMS, d, nk * FBK, c_base, tid);
             cp_async_commit();
         }
         if ((kt % FRESEED_TILES) == 0) {
-            double rp = (double)(kt * FBK + t) + cR;                     // R' of this lane's K slot
-#pragma unroll
-            for (int mb = 0; mb < 4; ++mb) cis_cycles(d.alpha, rp, up[mb], 1.0, tc_[mb], ts_[mb]);
+            const double rp = (double)(kt * FBK + t) + cR;               // R' of this lane's K slot
+            double sc, ss;
+            cis_cycles(d.alpha, rp, up0, 1.0, tc_[0], ts_[0]);
+            cis_cycles(d.alpha, rp, 8.0, 1.0, sc, ss);
+            cmul(tc_[0], ts_[0], sc, ss, tc_[1], ts_[1]);
         }
-        const double2 *se = sD + (kt % FSTAGES) * STAGE_ELEMS + wc * 16 + g;
+        const double2 *se = sD + (kt % FSTAGES) * STAGE_ELEMS + g;
         const double2 *so = se + FBK * FLDS;
 
 #pragma unroll
         for (int ks = 0; ks < FBK / 4; ++ks) {
-            double2 ve[2], vo[2];
+            double2 ve[4], vo[4];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
+            for (int q = 0; q < 4; ++q) {
                 ve[q] = se[(ks * 4 + t) * FLDS + q * 8];
                 vo[q] = so[(ks * 4 + t) * FLDS + q * 8];
             }
+            // next k-step's twiddles, issued ahead of this step's MMAs (separate registers)
+            double ntc[2], nts[2];
 #pragma unroll
-            for (int mb = 0; mb < 4; ++mb)
+            for (int mb = 0; mb < 2; ++mb) cmul(tc_[mb], ts_[mb], rc_[mb], rs_[mb], ntc[mb], nts[mb]);
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
+            for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
                     dmma884(accA[mb][q][0][0], accA[mb][q][0][1], tc_[mb], ve[q].x);
                     dmma884(accA[mb][q][1][0], accA[mb][q][1][1], tc_[mb], ve[q].y);
                 }
 #pragma unroll
-            for (int mb = 0; mb < 4; ++mb)
+            for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
+                for (int q = 0; q < 4; ++q) {
                     dmma884(accB[mb][q][0][0], accB[mb][q][0][1], ts_[mb], vo[q].x);
                     dmma884(accB[mb][q][1][0], accB[mb][q][1][1], ts_[mb], vo[q].y);
                 }
 #pragma unroll
-            for (int mb = 0; mb < 4; ++mb) {
-                double nc = tc_[mb] * rc_[mb] - ts_[mb] * rs_[mb];
-                double ns = tc_[mb] * rs_[mb] + ts_[mb] * rc_[mb];
-                tc_[mb] = nc;
-                ts_[mb] = ns;
+            for (int mb = 0; mb < 2; ++mb) {
+                tc_[mb] = ntc[mb];
+                ts_[mb] = nts[mb];
             }
         }
     }
     cp_async_wait<0>();
 
     // ---- epilogue: unfold to the +U' and -U' output rows, post phase, scale, transposed store ----
+    double ppc, pps, pmc, pms, stc, sts;
+    cis_cycles(d.alpha, d.oprime, up0 - d.sprime, d.sgn, ppc, pps);
+    cis_cycles(d.alpha, d.oprime, -up0 - d.sprime, d.sgn, pmc, pms);
+    cis_cycles(d.alpha, d.oprime, 8.0, d.sgn, stc, sts);
+    ppc *= d.scale; pps *= d.scale; pmc *= d.scale; pms *= d.scale;
+
+    // FOLD_OUT: pre2(R2') for the lane's four folded columns r2 = c_base + 8*qq + 2t + i
+    double p2c[2][2], p2s[2][2];
+    if (FOLD_OUT) {
+        double s1c, s1s, s8c, s8s;
+        const double r2p = (double)(c_base + 2 * t) + 0.5 * d.ncR2;
+        cis_cycles(d.nalpha, d.nsprime, r2p, -d.sgn, p2c[0][0], p2s[0][0]);
+        cis_cycles(d.nalpha, d.nsprime, 1.0, -d.sgn, s1c, s1s);
+        cis_cycles(d.nalpha, d.nsprime, 8.0, -d.sgn, s8c, s8s);
+        cmul(p2c[0][0], p2s[0][0], s1c, s1s, p2c[0][1], p2s[0][1]);
+        cmul(p2c[0][0], p2s[0][0], s8c, s8s, p2c[1][0], p2s[1][0]);
+        cmul(p2c[0][1], p2s[0][1], s8c, s8s, p2c[1][1], p2s[1][1]);
+    }
+
 #pragma unroll
-    for (int mb = 0; mb < 4; ++mb) {
-        const int u = r_base + wr * 32 + mb * 8 + g;
+    for (int mb = 0; mb < 2; ++mb) {
+        if (mb > 0) {
+            cmul(ppc, pps, stc, sts, ppc, pps);
+            cmul(pmc, pms, stc, -sts, pmc, pms);
+        }
+        const int u = r_base + warp * 16 + mb * 8 + g;
         if (u >= d.Rf) continue;
         const int kp = d.hM + u, km = d.hM - u - d.cU2;
         const bool has_p = kp < d.M;
         const bool has_m = (km >= 0) && !(d.cU2 == 0 && u == 0);
-        double ppc, pps, pmc, pms;
-        cis_cycles(d.alpha, d.oprime, up[mb] - d.sprime, d.sgn, ppc, pps);
-        cis_cycles(d.alpha, d.oprime, -up[mb] - d.sprime, d.sgn, pmc, pms);
-        ppc *= d.scale; pps *= d.scale; pmc *= d.scale; pms *= d.scale;
+
+        if (!FOLD_OUT) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
+            for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int c = c_base + wc * 16 + q * 8 + 2 * t + i;
-                if (c >= d.C) continue;
-                const double Ar = accA[mb][q][0][i], Ai = accA[mb][q][1][i];
-                const double Br = d.sgn * accB[mb][q][0][i], Bi = d.sgn * accB[mb][q][1][i];
-                double2 *col = d.O + (long long)c * d.ldo;
-                if (has_p) {   // A + i sgn B
-                    double xr = Ar - Bi, xi = Ai + Br;
-                    col[kp] = make_double2(xr * ppc - xi * pps, xr * pps + xi * ppc);
+                for (int i = 0; i < 2; ++i) {
+                    const int c = c_base + q * 8 + 2 * t + i;
+                    if (c >= d.C) continue;
+                    const double Ar = accA[mb][q][0][i], Ai = accA[mb][q][1][i];
+                    const double Br = d.sgn * accB[mb][q][0][i], Bi = d.sgn * accB[mb][q][1][i];
+                    double2 *col = d.O + (long long)c * d.ldo;
+                    if (has_p) {   // A + i sgn B
+                        double xr = Ar - Bi, xi = Ai + Br;
+                        col[kp] = make_double2(xr * ppc - xi * pps, xr * pps + xi * ppc);
+                    }
+                    if (has_m) {   // A - i sgn B
+                        double xr = Ar + Bi, xi = Ai - Br;
+                        col[km] = make_double2(xr * pmc - xi * pms, xr * pms + xi * pmc);
+                    }
                 }
-                if (has_m) {   // A - i sgn B
-                    double xr = Ar + Bi, xi = Ai - Br;
-                    col[km] = make_double2(xr * pmc - xi * pms, xr * pms + xi * pmc);
+        } else {
+#pragma unroll
+            for (int qq = 0; qq < 2; ++qq)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int r2 = c_base + qq * 8 + 2 * t + i;
+                    if (r2 >= d.nKf) continue;
+                    const bool center = (d.ncR2 == 0) && (r2 == 0);
+                    // column j+ lives in q = qq, its mirror j- in q = qq + 2
+                    const double Apr = accA[mb][qq][0][i], Api = accA[mb][qq][1][i];
+                    const double Bpr = d.sgn * accB[mb][qq][0][i], Bpi = d.sgn * accB[mb][qq][1][i];
+                    const double Amr = accA[mb][qq + 2][0][i], Ami = accA[mb][qq + 2][1][i];
+                    const double Bmr = d.sgn * accB[mb][qq + 2][0][i], Bmi = d.sgn * accB[mb][qq + 2][1][i];
+                    const double pc2 = p2c[qq][i], ps2 = p2s[qq][i];
+                    double2 *ge = d.O + (long long)r2 * d.nldg;
+                    double2 *go = d.O + ((long long)d.nKf + r2) * d.nldg;
+#pragma unroll
+                    for (int side = 0; side < 2; ++side) {
+                        if (side == 0 ? !has_p : !has_m) continue;
+                        const double sg = side == 0 ? 1.0 : -1.0;       // +U' row: A + i sgn B ; -U' row: A - i sgn B
+                        const double pc = side == 0 ? ppc : pmc, ps = side == 0 ? pps : pms;
+                        const int k = side == 0 ? kp : km;
+                        double xr, xi, tpr, tpi, tmr, tmi, gpr, gpi, gmr, gmi;
+                        xr = Apr - sg * Bpi; xi = Api + sg * Bpr;
+                        cmul(xr, xi, pc, ps, tpr, tpi);                   // T[k][j+]
+                        xr = Amr - sg * Bmi; xi = Ami + sg * Bmr;
+                        cmul(xr, xi, pc, ps, tmr, tmi);                   // T[k][j-]
+                        cmul(tpr, tpi, pc2, ps2, gpr, gpi);               // pre2 * T+
+                        cmul(tmr, tmi, pc2, -ps2, gmr, gmi);              // conj(pre2) * T-
+                        if (center) {
+                            ge[k] = make_double2(gpr, gpi);
+                            go[k] = make_double2(0.0, 0.0);
+                        } else {
+                            ge[k] = make_double2(gpr + gmr, gpi + gmi);
+                            go[k] = make_double2(gpr - gmr, gpi - gmi);
+                        }
+                    }
                 }
-            }
+        }
     }
 }
 
 static inline size_t f_align(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 size_t folded_workspace_bytes(const lfd_mft_desc *descs, int count) {
-    size_t bytes = f_align((size_t)2 * count * (sizeof(FoldDesc) + sizeof(FStageDesc)), 256);
+    size_t bytes = f_align((size_t)count * (sizeof(FoldDesc) + 2 * sizeof(FStageDesc)), 256);
     for (int i = 0; i < count; ++i) {
         const lfd_mft_desc &p = descs[i];
-        size_t g1 = (size_t)2 * ((p.m + 1) / 2) * p.n, g2 = (size_t)2 * ((p.n + 1) / 2) * p.M;
-        bytes += f_align((g1 > g2 ? g1 : g2) * sizeof(double2), 256);
-        bytes += f_align((size_t)p.n * p.M * sizeof(double2), 256);
+        bytes += f_align((size_t)2 * ((p.m + 1) / 2) * p.n * sizeof(double2), 256);
+        bytes += f_align((size_t)2 * ((p.n + 1) / 2) * p.M * sizeof(double2), 256);
     }
     return bytes;
 }
@@ -262,78 +347,80 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
     size_t need = folded_workspace_bytes(descs, count);
     LFD_REQUIRE(workspace_bytes >= need, "lfd_mft_c128_batched: workspace too small (%zu < %zu)",
                 workspace_bytes, need);
+    LFD_REQUIRE(count <= 65535, "lfd_mft_c128_batched: at most 65535 planes per call (got %d)", count);
     static bool attr_set = false;
     if (!attr_set) {
-        LFD_CUDA_OK(cudaFuncSetAttribute(mft_folded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        LFD_CUDA_OK(cudaFuncSetAttribute(mft_folded_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)FSMEM_BYTES));
+        LFD_CUDA_OK(cudaFuncSetAttribute(mft_folded_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)FSMEM_BYTES));
         attr_set = true;
     }
-    const size_t nfold = (size_t)2 * count, nstage = (size_t)2 * count;
-    const size_t hdr_bytes = nfold * sizeof(FoldDesc) + nstage * sizeof(FStageDesc);
+    const size_t hdr_bytes = (size_t)count * (sizeof(FoldDesc) + 2 * sizeof(FStageDesc));
     char *h = (char *)malloc(hdr_bytes);
     LFD_REQUIRE(h != nullptr, "out of host memory");
     FoldDesc *hf = (FoldDesc *)h;
-    FStageDesc *hs = (FStageDesc *)(h + nfold * sizeof(FoldDesc));
+    FStageDesc *hs = (FStageDesc *)(h + (size_t)count * sizeof(FoldDesc));
     char *ws = (char *)workspace;
     size_t off = f_align(hdr_bytes, 256);
-    int rows1 = 0, rows2 = 0, tiles1 = 0, tiles2 = 0;
+    int max_rows = 0, max_t1 = 0, max_t2 = 0;
     for (int i = 0; i < count; ++i) {
         const lfd_mft_desc &p = descs[i];
         if (!(p.m > 0 && p.n > 0 && p.M > 0 && p.N > 0 && p.ldf >= p.n && p.ldo >= p.N && p.f && p.out)) {
             free(h);
             LFD_REQUIRE(false, "lfd_mft_c128_batched: plane %d has invalid shape/ld/pointers", i);
         }
-        size_t g1 = (size_t)2 * ((p.m + 1) / 2) * p.n, g2 = (size_t)2 * ((p.n + 1) / 2) * p.M;
-        double2 *G = (double2 *)(ws + off);
-        off += f_align((g1 > g2 ? g1 : g2) * sizeof(double2), 256);
-        double2 *Tt = (double2 *)(ws + off);
-        off += f_align((size_t)p.n * p.M * sizeof(double2), 256);
+        const int Kf1 = (p.m + 1) / 2, Kf2 = (p.n + 1) / 2;
+        double2 *G1 = (double2 *)(ws + off);
+        off += f_align((size_t)2 * Kf1 * p.n * sizeof(double2), 256);
+        double2 *G2 = (double2 *)(ws + off);
+        off += f_align((size_t)2 * Kf2 * p.M * sizeof(double2), 256);
         const double sgn = p.inverse ? 1.0 : -1.0;
         double scale = p.unitary ? sqrt(fabs(p.alpha_r * p.alpha_c)) : 1.0;
         if (p.inverse) scale /= ((double)p.m * (double)p.n);
+        const int cRm = (p.m % 2 == 0), cRn = (p.n % 2 == 0), cUM = (p.M % 2 == 0), cUN = (p.N % 2 == 0);
 
-        for (int st = 0; st < 2; ++st) {
-            // stage 0: rows (K = m, C = n, out rows M); stage 1: columns (K = n, C = M, out rows N)
-            const int K = st == 0 ? p.m : p.n, C = st == 0 ? p.n : p.M, Mo = st == 0 ? p.M : p.N;
-            const double alpha = st == 0 ? p.alpha_r : p.alpha_c;
-            const double o = st == 0 ? p.off_r : p.off_c, s = st == 0 ? p.shift_r : p.shift_c;
-            const int cR2 = (K % 2 == 0) ? 1 : 0, cU2 = (Mo % 2 == 0) ? 1 : 0;
-            FoldDesc &fd = hf[st * count + i];
-            fd.D = st == 0 ? (const double2 *)p.f : Tt;
-            fd.ldd = st == 0 ? p.ldf : p.M;
-            fd.G = G;
-            fd.K = K; fd.C = C; fd.Kf = (K + 1) / 2; fd.hm = K / 2; fd.cR2 = cR2;
-            fd.alpha = alpha; fd.sprime = s + 0.5 * cU2; fd.sgn = sgn;
-            fd.row_base = st == 0 ? rows1 : rows2;
-            (st == 0 ? rows1 : rows2) += fd.Kf;
+        FoldDesc &fd = hf[i];
+        fd.D = (const double2 *)p.f; fd.ldd = p.ldf; fd.G = G1;
+        fd.K = p.m; fd.C = p.n; fd.Kf = Kf1; fd.hm = p.m / 2; fd.cR2 = cRm; fd.pad_ = 0;
+        fd.alpha = p.alpha_r; fd.sprime = p.shift_r + 0.5 * cUM; fd.sgn = sgn;
+        if (Kf1 > max_rows) max_rows = Kf1;
 
-            FStageDesc &sd = hs[st * count + i];
-            sd.G = G;
-            sd.O = st == 0 ? Tt : (double2 *)p.out;
-            sd.ldo = st == 0 ? p.M : p.ldo;
-            sd.Kf = fd.Kf; sd.C = C; sd.Rf = (Mo + 1) / 2; sd.M = Mo; sd.hM = Mo / 2;
-            sd.cR2 = cR2; sd.cU2 = cU2;
-            sd.alpha = alpha; sd.oprime = o - 0.5 * cR2; sd.sprime = s + 0.5 * cU2;
-            sd.scale = st == 0 ? 1.0 : scale; sd.sgn = sgn;
-            sd.tiles_r = (sd.Rf + FBR - 1) / FBR; sd.tiles_c = (C + FBC - 1) / FBC;
-            sd.tile_base = st == 0 ? tiles1 : tiles2;
-            (st == 0 ? tiles1 : tiles2) += sd.tiles_r * sd.tiles_c;
-        }
+        // stage 1 (rows): K = m, C = n, output rows M; result folded along its columns for stage 2
+        FStageDesc &s1 = hs[i];
+        s1.G = G1; s1.O = G2; s1.ldo = 0;
+        s1.Kf = Kf1; s1.C = p.n; s1.Rf = (p.M + 1) / 2; s1.M = p.M; s1.hM = p.M / 2;
+        s1.cR2 = cRm; s1.cU2 = cUM;
+        s1.alpha = p.alpha_r; s1.oprime = p.off_r - 0.5 * cRm; s1.sprime = p.shift_r + 0.5 * cUM;
+        s1.scale = 1.0; s1.sgn = sgn;
+        s1.nKf = Kf2; s1.nhm = p.n / 2; s1.ncR2 = cRn; s1.nldg = p.M;
+        s1.nalpha = p.alpha_c; s1.nsprime = p.shift_c + 0.5 * cUN;
+        s1.tiles_r = (s1.Rf + FBR - 1) / FBR; s1.tiles_c = (Kf2 + FBC / 2 - 1) / (FBC / 2);
+        if (s1.tiles_r * s1.tiles_c > max_t1) max_t1 = s1.tiles_r * s1.tiles_c;
+
+        // stage 2 (columns): K = n, C = M, output rows N -> out (M x N after the transposed store)
+        FStageDesc &s2 = hs[count + i];
+        s2.G = G2; s2.O = (double2 *)p.out; s2.ldo = p.ldo;
+        s2.Kf = Kf2; s2.C = p.M; s2.Rf = (p.N + 1) / 2; s2.M = p.N; s2.hM = p.N / 2;
+        s2.cR2 = cRn; s2.cU2 = cUN;
+        s2.alpha = p.alpha_c; s2.oprime = p.off_c - 0.5 * cRn; s2.sprime = p.shift_c + 0.5 * cUN;
+        s2.scale = scale; s2.sgn = sgn;
+        s2.nKf = 0; s2.nhm = 0; s2.ncR2 = 0; s2.nldg = 0; s2.nalpha = 0.0; s2.nsprime = 0.0;
+        s2.tiles_r = (s2.Rf + FBR - 1) / FBR; s2.tiles_c = (s2.C + FBC - 1) / FBC;
+        if (s2.tiles_r * s2.tiles_c > max_t2) max_t2 = s2.tiles_r * s2.tiles_c;
     }
     cudaError_t e = cudaMemcpyAsync(workspace, h, hdr_bytes, cudaMemcpyHostToDevice, stream);
     free(h);
     LFD_CUDA_OK(e);
     const FoldDesc *df = (const FoldDesc *)workspace;
-    const FStageDesc *ds = (const FStageDesc *)((char *)workspace + nfold * sizeof(FoldDesc));
-    fold_kernel<<<rows1, 256, 0, stream>>>(df, count);
+    const FStageDesc *ds = (const FStageDesc *)((char *)workspace + (size_t)count * sizeof(FoldDesc));
+    fold_kernel<<<dim3(max_rows, count), 256, 0, stream>>>(df);
     LFD_CUDA_OK(cudaGetLastError());
-    mft_folded_kernel<<<tiles1, FTHREADS, FSMEM_BYTES, stream>>>(ds, count);
+    mft_folded_kernel<true><<<dim3(max_t1, count), FTHREADS, FSMEM_BYTES, stream>>>(ds);
     LFD_CUDA_OK(cudaGetLastError());
-    fold_kernel<<<rows2, 256, 0, stream>>>(df + count, count);
+    mft_folded_kernel<false><<<dim3(max_t2, count), FTHREADS, FSMEM_BYTES, stream>>>(ds + count);
     LFD_CUDA_OK(cudaGetLastError());
-    mft_folded_kernel<<<tiles2, FTHREADS, FSMEM_BYTES, stream>>>(ds + count, count);
-    LFD_CUDA_OK(cudaGetLastError());
-    count_launch(4);
+    count_launch(3);
     return 0;
 }
 
