@@ -195,6 +195,20 @@ def accumulate_intensity(fields, out_dev, groups=None, weights=None):
     return out_dev
 
 
+def accumulate_windows(wins, out_dev):
+    """K3 on a prepared numpy table of lfd_window rows (dtype np.dtype(_lib.Window))."""
+    n = len(wins)
+    if n == 0:
+        return out_dev
+    H, W = int(out_dev.shape[0]), int(out_dev.shape[1])
+    scratch = device.empty_bytes(C.sizeof(_lib.Window) * n)
+    rc = _lib.lib().lfd_accum_intensity(wins.ctypes.data_as(C.POINTER(_lib.Window)), n, out_dev.data_ptr(),
+                                        H, W, device.ld_of(out_dev), scratch.data_ptr(), scratch.numel(),
+                                        device.stream_ptr())
+    _lib.check(rc, "lfd_accum_intensity")
+    return out_dev
+
+
 def accumulate_field(fields, out_dev, weights=None):
     """out_dev (complex) += weight * field  for each field (lentil/field.py:303-304)."""
     fields = [f for f in fields if f.size > 0]

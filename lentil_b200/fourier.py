@@ -38,7 +38,7 @@ TIMERS = None
 
 def mft_flops(descs, count):
     """Algorithmic flops of a batch, 8*M*n*(m+N) per plane."""
-    return float(sum(8.0 * d.M * d.n * (d.m + d.N) for d in descs[:count]))
+    return float(sum(8.0 * descs[i].M * descs[i].n * (descs[i].m + descs[i].N) for i in range(count)))
 
 
 def run_mft(descs, count):

@@ -210,7 +210,12 @@ class Plane(_PlaneBase):
         multiply, or once per freeze() when the plane is frozen."""
         if self.frozen and self._dev_cache is not None:
             return self._dev_cache
-        amp, opd, mask = np.asarray(self.amplitude), np.asarray(self.opd), np.asarray(self.mask)
+        amp, opd = np.asarray(self.amplitude), np.asarray(self.opd)
+        # When the mask is the default one derived from the amplitude (plane.py:43-47:
+        # amplitude.astype(bool)) then amp*mask == amp, so K1 needs no mask plane and only the
+        # bounding box has to be found (same pixels: amp != 0).
+        derived = self._mask is None and type(self).__mask__ is _PlaneBase.__mask__
+        mask = (amp != 0) if derived else np.asarray(self.mask)
         nseg = 1 if mask.ndim < 3 else mask.shape[0]
         shape = tuple(mask.shape) if nseg == 1 else tuple(mask.shape[1:])
         slices = _plane_slice(mask)
@@ -220,7 +225,7 @@ class Plane(_PlaneBase):
         else:
             if len(shape) != 2:
                 raise ValueError('array amplitude/opd need a 2-D (or 3-D segment) mask')
-            use_mask = amp.size != 1       # plane.py:503 — a scalar amplitude is not masked
+            use_mask = amp.size != 1 and not derived   # plane.py:503 — a scalar amplitude is not masked
             if use_mask:
                 mk = mask.reshape((nseg,) + shape)
                 binary = mk.dtype == bool or np.all((mk == 0) | (mk == 1))
@@ -228,8 +233,8 @@ class Plane(_PlaneBase):
                     if nseg > 1:
                         raise NotImplementedError('non-binary segment masks are not supported')
                     amp, use_mask = amp * mk[0], False
-            ops['amp'] = device.to_dev(np.broadcast_to(amp, shape), dtype=np.float64)
-            ops['opd'] = device.to_dev(np.broadcast_to(opd, shape), dtype=np.float64)
+            ops['amp'] = device.to_dev(amp if amp.shape == shape else np.broadcast_to(amp, shape), dtype=np.float64)
+            ops['opd'] = device.to_dev(opd if opd.shape == shape else np.broadcast_to(opd, shape), dtype=np.float64)
             ops['mask'] = device.to_dev(mk.astype(np.uint8)) if use_mask else None
             segs = (_lib.Segment * nseg)()
             total = 0
@@ -248,10 +253,10 @@ class Plane(_PlaneBase):
             self._dev_cache = ops
         return ops
 
-    def _phasors(self, wavelengths):
+    def _phasors(self, wavelengths, ops=None):
         """K1: phasor tiles for a list of wavelengths.  Returns a (nlam, total) complex128 device
         buffer; segment k of wavelength l is buf[l, off_k : off_k + h_k*w_k] viewed (h_k, w_k)."""
-        ops = self._operands()
+        ops = self._operands() if ops is None else ops
         lam = np.ascontiguousarray(wavelengths, dtype=np.float64).reshape(-1)
         buf = device.empty_c128(len(lam), ops['total'])
         rc = _lib.lib().lfd_pupil_prep(
@@ -290,7 +295,7 @@ class Plane(_PlaneBase):
                              tilt=[self.tilt[n]] if self.tilt else [])
                        for n, s in enumerate(ops['slices'])]
         else:
-            _, buf = self._phasors([wavefront.wavelength])
+            _, buf = self._phasors([wavefront.wavelength], ops)
             phasors = [Field(self._segment_view(ops, buf[0], n), pixelscale=self.pixelscale,
                              offset=ops['offsets'][n], tilt=[self.tilt[n]] if self.tilt else [])
                        for n in range(ops['nseg'])]

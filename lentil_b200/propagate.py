@@ -11,6 +11,8 @@ ONE batched K2a launch pair (lfd_mft_c128_batched).
 host and executed as K1 -> K2a -> K3 over whole chunks of planes, with the pupil resident in
 HBM and the PSF stack accumulated on the device.
 """
+import ctypes as C
+
 import numpy as np
 
 from . import _lib, device, extent as _extent, helper
@@ -157,6 +159,9 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
     out : optional float64 device tensor to accumulate into (shape (P, H, W) or (H, W))
     distributed : shard the wavelengths over torch.distributed ranks and all-reduce the stack
     return_device : return the device tensor instead of a numpy array
+
+    Host work is O(field points x segments) window planning plus numpy-vectorised descriptor
+    tables (one row per plane); everything per-pixel runs in K1 / K2a / K3.
     """
     from .plane import Tilt
     wavelengths = np.asarray(wavelengths, dtype=float).reshape(-1)
@@ -184,59 +189,113 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
     du = np.broadcast_to(pixelscale, (2,))
     z = getattr(plane, 'focal_length', None)
 
-    rank, world = 0, 1
-    if distributed:
-        import torch.distributed as dist
-        rank, world = dist.get_rank(), dist.get_world_size()
-    my = np.arange(L)[rank::world] if world > 1 else np.arange(L)
-
+    my = shard_indices(L, distributed)
     stack = out if out is not None else device.zeros_f64(P, H, W)
     stack3 = stack.view(P, H, W)
 
     nseg = ops['nseg']
+    segs = ops['segs']
     seg_tilts = [[plane.tilt[n]] if plane.tilt else [] for n in range(nseg)]
-    # bytes per wavelength: phasors + (transposed intermediate + output window) per field point
+    pairs = [(p, n, ([points[p]] if points[p] is not None else []) + seg_tilts[n])
+             for p in range(P) for n in range(nseg)]
+    # plain Tilt objects shift by the same number of pixels at every wavelength: plan once
+    static = all(type(t) is Tilt for _, _, tl in pairs for t in tl)
+    # bytes per wavelength: phasors + (folded intermediates + output window) per field point
     per_lam = 16 * ops['total'] + P * sum(
-        16 * (int(ops['segs'][n].w) * int(prop_shape_out[0]) + int(prop_shape_out[0]) * int(prop_shape_out[1]))
+        16 * (2 * int(segs[n].w) * int(prop_shape_out[0]) + int(prop_shape_out[0]) * int(prop_shape_out[1]))
         for n in range(nseg))
     step = max(1, int(chunk_bytes // max(per_lam, 1)))
+
+    seg_off = np.array([segs[n].out_offset for n in range(nseg)], dtype=np.int64)
+    seg_h = np.array([segs[n].h for n in range(nseg)], dtype=np.int64)
+    seg_w = np.array([segs[n].w for n in range(nseg)], dtype=np.int64)
+    offs = np.array(ops['offsets'], dtype=float).reshape(nseg, 2)
+    alpha_num = (dx[0] * du[0], dx[1] * du[1])
 
     for c0 in range(0, len(my), step):
         idx = my[c0:c0 + step]
         lam = wavelengths[idx]
-        _, phasors = plane._phasors(lam)                                   # K1
-        jobs = []       # (l, p, n, plan)
-        for li, wl in enumerate(lam):
-            for p, pt in enumerate(points):
-                for n in range(nseg):
-                    tl = ([pt] if pt is not None else []) + seg_tilts[n]
-                    plan = plan_window(_shift_for(tl, z, wl, du, oversample), prop_shape_out, out_extent)
-                    if plan is not None:
-                        jobs.append((li, p, n, plan))
-        if not jobs:
+        nl = len(lam)
+        _, phasors = plane._phasors(lam, ops)                               # K1
+        # ---- window planning: rows (li, p, n) -> window shape / offset / dft shift -----------------
+        if static:
+            plans = [plan_window(_shift_for(tl, z, lam[0], du, oversample), prop_shape_out, out_extent)
+                     for _, _, tl in pairs]
+            keep = [k for k, pl in enumerate(plans) if pl is not None]
+            jp = np.tile(np.array([pairs[k][0] for k in keep], dtype=np.int64), nl)
+            jn = np.tile(np.array([pairs[k][1] for k in keep], dtype=np.int64), nl)
+            jl = np.repeat(np.arange(nl, dtype=np.int64), len(keep))
+            jshape = np.tile(np.array([plans[k][0] for k in keep], dtype=np.int64).reshape(-1, 2), (nl, 1))
+            jshift = np.tile(np.array([plans[k][1] for k in keep], dtype=np.int64).reshape(-1, 2), (nl, 1))
+            jdft = np.tile(np.array([plans[k][2] for k in keep], dtype=float).reshape(-1, 2), (nl, 1))
+        else:
+            rows = []
+            for li, wl in enumerate(lam):
+                for p, n, tl in pairs:
+                    pl = plan_window(_shift_for(tl, z, wl, du, oversample), prop_shape_out, out_extent)
+                    if pl is not None:
+                        rows.append((li, p, n, pl))
+            jl = np.array([r[0] for r in rows], dtype=np.int64)
+            jp = np.array([r[1] for r in rows], dtype=np.int64)
+            jn = np.array([r[2] for r in rows], dtype=np.int64)
+            jshape = np.array([r[3][0] for r in rows], dtype=np.int64).reshape(-1, 2)
+            jshift = np.array([r[3][1] for r in rows], dtype=np.int64).reshape(-1, 2)
+            jdft = np.array([r[3][2] for r in rows], dtype=float).reshape(-1, 2)
+        nj = len(jl)
+        if nj == 0:
             continue
-        total = sum(int(j[3][0][0]) * int(j[3][0][1]) for j in jobs)
-        buf = device.empty_c128(total)
-        descs = (_lib.MftDesc * len(jobs))()
-        fields_by_point = [[] for _ in range(P)]
-        pos = 0
-        for k, (li, p, n, (ishape, ishift, dshift)) in enumerate(jobs):
-            h, w = int(ishape[0]), int(ishape[1])
-            win = buf[pos:pos + h * w].view(h, w)
-            pos += h * w
-            alpha = _dft_alpha(dx=dx, du=du, z=z, wavelength=lam[li], oversample=oversample)
-            _fourier.mft_descriptor(descs[k], plane._segment_view(ops, phasors[li], n), win, alpha,
-                                    dshift, ops['offsets'][n], unitary=True)
-            fields_by_point[p].append((li, Field(win, offset=ishift)))
-        _fourier.run_mft(descs, len(jobs))                                 # K2a
-        for p in range(P):                                                 # K3
-            fl = fields_by_point[p]
-            if fl:
-                _field.accumulate_intensity([f for _, f in fl], stack3[p], [li for li, _ in fl],
-                                            [float(weights[idx[li]]) for li, _ in fl])
+        sizes = jshape[:, 0] * jshape[:, 1]
+        pos = np.concatenate(([0], np.cumsum(sizes)[:-1]))
+        buf = device.empty_c128(int(sizes.sum()))
+        # ---- K2a descriptors, one row per plane -------------------------------------------------
+        D = np.zeros(nj, dtype=np.dtype(_lib.MftDesc))
+        D['f'] = phasors.data_ptr() + 16 * (jl * ops['total'] + seg_off[jn])
+        D['ldf'] = seg_w[jn]
+        D['out'] = buf.data_ptr() + 16 * pos
+        D['ldo'] = jshape[:, 1]
+        D['m'], D['n'] = seg_h[jn], seg_w[jn]
+        D['M'], D['N'] = jshape[:, 0], jshape[:, 1]
+        D['alpha_r'] = alpha_num[0] / (lam[jl] * z * oversample)
+        D['alpha_c'] = alpha_num[1] / (lam[jl] * z * oversample)
+        D['shift_r'], D['shift_c'] = jdft[:, 0], jdft[:, 1]
+        D['off_r'], D['off_c'] = offs[jn, 0], offs[jn, 1]
+        D['unitary'] = 1
+        _fourier.run_mft(D.ctypes.data_as(C.POINTER(_lib.MftDesc)), nj)      # K2a
+        # ---- K3: per field point, groups = wavelengths ---------------------------------------------
+        Wn = np.zeros(nj, dtype=np.dtype(_lib.Window))
+        Wn['E'], Wn['ld'] = D['out'], jshape[:, 1]
+        Wn['h'], Wn['w'] = jshape[:, 0], jshape[:, 1]
+        Wn['r0'] = H // 2 - jshape[:, 0] // 2 + jshift[:, 0]      # lentil/field.py:267-268
+        Wn['c0'] = W // 2 - jshape[:, 1] // 2 + jshift[:, 1]
+        Wn['group'] = jl
+        Wn['weight'] = weights[idx][jl]
+        for p in range(P):
+            sel = Wn[jp == p] if P > 1 else Wn
+            if len(sel):
+                _field.accumulate_windows(np.ascontiguousarray(sel), stack3[p])
 
-    if distributed and world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(stack, op=dist.ReduceOp.SUM)
+    if distributed:
+        reduce_stack(stack)
     result = stack3[0] if squeeze else stack3
     return result if return_device else device.to_host(result)
+
+
+def shard_indices(L, distributed=False, rank=None, world=None):
+    """Wavelength indices this rank owns: a strided deal of range(L) over the ranks of
+    torch.distributed (all of them when not distributed).  Strided so that every rank sees the
+    whole spectral range (window sizes, and so the work per plane, can vary with wavelength)."""
+    if not distributed:
+        return np.arange(L)
+    if rank is None or world is None:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+    return np.arange(L)[rank::world]
+
+
+def reduce_stack(stack):
+    """Sum the per-rank PSF stacks in place (NCCL all-reduce over NVLink on GPUs; gloo in the CPU
+    tests).  The only collective on the path: planes are independent until the incoherent sum."""
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(stack, op=dist.ReduceOp.SUM)
+    return stack
