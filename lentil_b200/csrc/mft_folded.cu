@@ -44,6 +44,7 @@ constexpr int FTHREADS = 128;  // 4 warps stacked along the rows, each 16 folded
                                // (a twiddle element feeds 8 DMMAs); two CTAs per SM so that one CTA's
                                // prologue / epilogue hides under the other's MMAs
 constexpr int FRESEED_TILES = 64;  // re-seed the twiddle recurrence every 1024 folded K (2048 input rows)
+constexpr int FIRST_WAVE_SMS = 148;  // B200: CTAs with linear id < 2*148 form the first wave
 constexpr size_t FSMEM_BYTES = (size_t)FSTAGES * 2 * FBK * FLDS * sizeof(double2);
 
 struct FoldDesc {
@@ -64,7 +65,54 @@ struct FStageDesc {
     long long nldg;
     double alpha, oprime, sprime, scale, sgn;
     double nalpha, nsprime;
+    // per-(plane, stage) phase tables built by phase_table_kernel, so that no CTA spends FP64
+    // pipe time on sincospi:  rot[Rfp] | seed[4][Rfp] | post+[Rfp] | post-[Rfp] | pre2[nKfp]
+    const double2 *tab;
+    int Rfp, nKfp;
+    // de-phasing of the two CTAs that share an SM (see mft_folded_kernel): per-launch slot counters
+    // (one per SM, zeroed with the descriptor upload) and the skew in cycles (~ half a tile)
+    unsigned *sm_slots;
+    long long skew_cycles;
 };
+
+__host__ __device__ inline size_t table_elems(int Rfp, int nKfp) { return (size_t)7 * Rfp + nKfp; }
+
+// one thread per table entry
+__global__ void __launch_bounds__(256)
+phase_table_kernel(const FStageDesc *__restrict__ descs) {
+    const FStageDesc d = descs[blockIdx.y];
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = (int)table_elems(d.Rfp, d.nKfp);
+    if (e >= n) return;
+    double2 *tab = const_cast<double2 *>(d.tab);
+    const double cR = 0.5 * d.cR2, cU = 0.5 * d.cU2;
+    const int sec = e / d.Rfp, u = e % d.Rfp;
+    const double up = (double)u + cU;
+    double c, s;
+    if (sec == 0) {
+        cis_cycles(d.alpha, 4.0, up, 1.0, c, s);                       // rotation for K += 4
+    } else if (sec <= 4) {
+        cis_cycles(d.alpha, (double)(sec - 1) + cR, up, 1.0, c, s);    // twiddle seed at K slot t = sec-1
+    } else if (sec == 5) {
+        cis_cycles(d.alpha, d.oprime, up - d.sprime, d.sgn, c, s);     // post(+U')
+        c *= d.scale; s *= d.scale;
+    } else if (sec == 6) {
+        cis_cycles(d.alpha, d.oprime, -up - d.sprime, d.sgn, c, s);    // post(-U')
+        c *= d.scale; s *= d.scale;
+    } else {
+        const int r2 = e - 7 * d.Rfp;
+        cis_cycles(d.nalpha, d.nsprime, (double)r2 + 0.5 * d.ncR2, -d.sgn, c, s);   // pre2(R2')
+    }
+    tab[e] = make_double2(c, s);
+}
+
+#ifdef LFD_TILE_TIMING
+// diagnostic build only: per-CTA timeline (entry, loop start, loop end, exit, smid) of lane 0 of warp 0
+__device__ long long *g_tile_timing = nullptr;
+#define LFD_TT(slot) if (g_tile_timing && threadIdx.x == 0) tt[slot] = clock64();
+#else
+#define LFD_TT(slot)
+#endif
 
 // z = x * y (complex)
 __device__ __forceinline__ void cmul(double xr, double xi, double yr, double yi, double &zr, double &zi) {
@@ -143,8 +191,28 @@ mft_folded_kernel(const FStageDesc *__restrict__ descs) {
     double2 *sD = reinterpret_cast<double2 *>(smem_raw);
     constexpr int STAGE_ELEMS = 2 * FBK * FLDS;
 
+#ifdef LFD_TILE_TIMING
+    long long tt[4];
+#endif
+    LFD_TT(0)
     const FStageDesc d = descs[blockIdx.y];
     const int tile = blockIdx.x;
+    // Two CTAs share an SM and every tile of a batch takes the same time, so left alone they run in
+    // lockstep and their prologues/epilogues (no MMAs) coincide.  The second CTA to arrive on an SM
+    // in the first wave waits half a tile once; the offset then persists for the whole launch.
+    if (blockIdx.y * gridDim.x + blockIdx.x < 2 * FIRST_WAVE_SMS) {
+        __shared__ unsigned s_slot;
+        if (threadIdx.x == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            s_slot = atomicAdd(d.sm_slots + (smid & 255), 1u);
+        }
+        __syncthreads();
+        if (s_slot & 1u) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < d.skew_cycles) __nanosleep(2000);
+        }
+    }
     if (tile >= d.tiles_r * d.tiles_c) return;
     const int tr = tile % d.tiles_r, tc = tile / d.tiles_r;
     const int r_base = tr * FBR;
@@ -177,22 +245,31 @@ mft_folded_kernel(const FStageDesc *__restrict__ descs) {
     double tc_[2], ts_[2], rc_[2], rs_[2];
     const double cR = 0.5 * d.cR2, cU = 0.5 * d.cU2;
     const double up0 = (double)(r_base + warp * 16 + g) + cU;            // U' of this lane's first row
-    {
-        double sc, ss;
-        cis_cycles(d.alpha, 4.0, up0, 1.0, rc_[0], rs_[0]);
-        cis_cycles(d.alpha, 4.0, 8.0, 1.0, sc, ss);
-        cmul(rc_[0], rs_[0], sc, ss, rc_[1], rs_[1]);
+    const int u0 = r_base + warp * 16 + g;
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) {
+        const double2 v = d.tab[u0 + 8 * mb];
+        rc_[mb] = v.x;
+        rs_[mb] = v.y;
     }
 
     for (int kt = 0; kt < KT; ++kt) {
         cp_async_wait<FSTAGES - 2>();
         __syncthreads();
+        if (kt == 0) { LFD_TT(1) }
         {
             int nk = kt + FSTAGES - 1;
             if (nk < KT) f_load_tile<FOLD_OUT>(sD + (nk % FSTAGES) * STAGE_ELEMS, d, nk * FBK, c_base, tid);
             cp_async_commit();
         }
-        if ((kt % FRESEED_TILES) == 0) {
+        if (kt == 0) {
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) {
+                const double2 v = d.tab[(size_t)(1 + t) * d.Rfp + u0 + 8 * mb];
+                tc_[mb] = v.x;
+                ts_[mb] = v.y;
+            }
+        } else if ((kt % FRESEED_TILES) == 0) {                          // very long K only
             const double rp = (double)(kt * FBK + t) + cR;               // R' of this lane's K slot
             double sc, ss;
             cis_cycles(d.alpha, rp, up0, 1.0, tc_[0], ts_[0]);
@@ -236,33 +313,26 @@ mft_folded_kernel(const FStageDesc *__restrict__ descs) {
         }
     }
     cp_async_wait<0>();
+    LFD_TT(2)
 
     // ---- epilogue: unfold to the +U' and -U' output rows, post phase, scale, transposed store ----
-    double ppc, pps, pmc, pms, stc, sts;
-    cis_cycles(d.alpha, d.oprime, up0 - d.sprime, d.sgn, ppc, pps);
-    cis_cycles(d.alpha, d.oprime, -up0 - d.sprime, d.sgn, pmc, pms);
-    cis_cycles(d.alpha, d.oprime, 8.0, d.sgn, stc, sts);
-    ppc *= d.scale; pps *= d.scale; pmc *= d.scale; pms *= d.scale;
-
     // FOLD_OUT: pre2(R2') for the lane's four folded columns r2 = c_base + 8*qq + 2t + i
     double p2c[2][2], p2s[2][2];
     if (FOLD_OUT) {
-        double s1c, s1s, s8c, s8s;
-        const double r2p = (double)(c_base + 2 * t) + 0.5 * d.ncR2;
-        cis_cycles(d.nalpha, d.nsprime, r2p, -d.sgn, p2c[0][0], p2s[0][0]);
-        cis_cycles(d.nalpha, d.nsprime, 1.0, -d.sgn, s1c, s1s);
-        cis_cycles(d.nalpha, d.nsprime, 8.0, -d.sgn, s8c, s8s);
-        cmul(p2c[0][0], p2s[0][0], s1c, s1s, p2c[0][1], p2s[0][1]);
-        cmul(p2c[0][0], p2s[0][0], s8c, s8s, p2c[1][0], p2s[1][0]);
-        cmul(p2c[0][1], p2s[0][1], s8c, s8s, p2c[1][1], p2s[1][1]);
+#pragma unroll
+        for (int qq = 0; qq < 2; ++qq)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const double2 v = d.tab[(size_t)7 * d.Rfp + c_base + qq * 8 + 2 * t + i];
+                p2c[qq][i] = v.x;
+                p2s[qq][i] = v.y;
+            }
     }
 
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb) {
-        if (mb > 0) {
-            cmul(ppc, pps, stc, sts, ppc, pps);
-            cmul(pmc, pms, stc, -sts, pmc, pms);
-        }
+        const double2 pp = d.tab[(size_t)5 * d.Rfp + u0 + 8 * mb], pm = d.tab[(size_t)6 * d.Rfp + u0 + 8 * mb];
+        const double ppc = pp.x, pps = pp.y, pmc = pm.x, pms = pm.y;      // scale folded in
         const int u = r_base + warp * 16 + mb * 8 + g;
         if (u >= d.Rf) continue;
         const int kp = d.hM + u, km = d.hM - u - d.cU2;
@@ -328,16 +398,29 @@ mft_folded_kernel(const FStageDesc *__restrict__ descs) {
                 }
         }
     }
+#ifdef LFD_TILE_TIMING
+    if (g_tile_timing && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        long long *o = g_tile_timing + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 6;
+        o[0] = tt[0]; o[1] = tt[1]; o[2] = tt[2]; o[3] = clock64(); o[4] = smid; o[5] = FOLD_OUT;
+    }
+#endif
 }
 
 static inline size_t f_align(size_t v, size_t a) { return (v + a - 1) / a * a; }
+constexpr long long SKEW_CYCLES_PER_KTILE = 2400;   // half of the ~4.7k cycles two co-resident CTAs spend per k-tile
+constexpr size_t SLOT_BYTES = 2 * 256 * sizeof(unsigned);   // per-SM slot counters, one set per MFT launch
 
 size_t folded_workspace_bytes(const lfd_mft_desc *descs, int count) {
-    size_t bytes = f_align((size_t)count * (sizeof(FoldDesc) + 2 * sizeof(FStageDesc)), 256);
+    size_t bytes = f_align((size_t)count * (sizeof(FoldDesc) + 2 * sizeof(FStageDesc)) + SLOT_BYTES, 256);
     for (int i = 0; i < count; ++i) {
         const lfd_mft_desc &p = descs[i];
         bytes += f_align((size_t)2 * ((p.m + 1) / 2) * p.n * sizeof(double2), 256);
         bytes += f_align((size_t)2 * ((p.n + 1) / 2) * p.M * sizeof(double2), 256);
+        const int Rfp1 = ((p.M + 1) / 2 + FBR - 1) / FBR * FBR, Rfp2 = ((p.N + 1) / 2 + FBR - 1) / FBR * FBR;
+        const int nKfp = ((p.n + 1) / 2 + FBC / 2 - 1) / (FBC / 2) * (FBC / 2);
+        bytes += f_align((table_elems(Rfp1, nKfp) + table_elems(Rfp2, 0)) * sizeof(double2), 256);
     }
     return bytes;
 }
@@ -347,7 +430,7 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
     size_t need = folded_workspace_bytes(descs, count);
     LFD_REQUIRE(workspace_bytes >= need, "lfd_mft_c128_batched: workspace too small (%zu < %zu)",
                 workspace_bytes, need);
-    LFD_REQUIRE(count <= 65535, "lfd_mft_c128_batched: at most 65535 planes per call (got %d)", count);
+    LFD_REQUIRE(count <= 32767, "lfd_mft_c128_batched: at most 32767 planes per call (got %d)", count);
     static bool attr_set = false;
     if (!attr_set) {
         LFD_CUDA_OK(cudaFuncSetAttribute(mft_folded_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -356,14 +439,16 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
                                          (int)FSMEM_BYTES));
         attr_set = true;
     }
-    const size_t hdr_bytes = (size_t)count * (sizeof(FoldDesc) + 2 * sizeof(FStageDesc));
-    char *h = (char *)malloc(hdr_bytes);
+    const size_t desc_bytes = (size_t)count * (sizeof(FoldDesc) + 2 * sizeof(FStageDesc));
+    const size_t hdr_bytes = desc_bytes + SLOT_BYTES;
+    char *h = (char *)calloc(hdr_bytes, 1);                 // slot counters start at zero
     LFD_REQUIRE(h != nullptr, "out of host memory");
     FoldDesc *hf = (FoldDesc *)h;
     FStageDesc *hs = (FStageDesc *)(h + (size_t)count * sizeof(FoldDesc));
+    unsigned *slots_dev = (unsigned *)((char *)workspace + desc_bytes);
     char *ws = (char *)workspace;
     size_t off = f_align(hdr_bytes, 256);
-    int max_rows = 0, max_t1 = 0, max_t2 = 0;
+    int max_rows = 0, max_t1 = 0, max_t2 = 0, max_tab = 0;
     for (int i = 0; i < count; ++i) {
         const lfd_mft_desc &p = descs[i];
         if (!(p.m > 0 && p.n > 0 && p.M > 0 && p.N > 0 && p.ldf >= p.n && p.ldo >= p.N && p.f && p.out)) {
@@ -375,6 +460,13 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
         off += f_align((size_t)2 * Kf1 * p.n * sizeof(double2), 256);
         double2 *G2 = (double2 *)(ws + off);
         off += f_align((size_t)2 * Kf2 * p.M * sizeof(double2), 256);
+        const int Rfp1 = ((p.M + 1) / 2 + FBR - 1) / FBR * FBR, Rfp2 = ((p.N + 1) / 2 + FBR - 1) / FBR * FBR;
+        const int nKfp = (Kf2 + FBC / 2 - 1) / (FBC / 2) * (FBC / 2);
+        double2 *tab1 = (double2 *)(ws + off);
+        double2 *tab2 = tab1 + table_elems(Rfp1, nKfp);
+        off += f_align((table_elems(Rfp1, nKfp) + table_elems(Rfp2, 0)) * sizeof(double2), 256);
+        if ((int)table_elems(Rfp1, nKfp) > max_tab) max_tab = (int)table_elems(Rfp1, nKfp);
+        if ((int)table_elems(Rfp2, 0) > max_tab) max_tab = (int)table_elems(Rfp2, 0);
         const double sgn = p.inverse ? 1.0 : -1.0;
         double scale = p.unitary ? sqrt(fabs(p.alpha_r * p.alpha_c)) : 1.0;
         if (p.inverse) scale /= ((double)p.m * (double)p.n);
@@ -395,6 +487,8 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
         s1.scale = 1.0; s1.sgn = sgn;
         s1.nKf = Kf2; s1.nhm = p.n / 2; s1.ncR2 = cRn; s1.nldg = p.M;
         s1.nalpha = p.alpha_c; s1.nsprime = p.shift_c + 0.5 * cUN;
+        s1.tab = tab1; s1.Rfp = Rfp1; s1.nKfp = nKfp;
+        s1.sm_slots = slots_dev; s1.skew_cycles = (long long)((Kf1 + FBK - 1) / FBK) * SKEW_CYCLES_PER_KTILE;
         s1.tiles_r = (s1.Rf + FBR - 1) / FBR; s1.tiles_c = (Kf2 + FBC / 2 - 1) / (FBC / 2);
         if (s1.tiles_r * s1.tiles_c > max_t1) max_t1 = s1.tiles_r * s1.tiles_c;
 
@@ -406,6 +500,8 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
         s2.alpha = p.alpha_c; s2.oprime = p.off_c - 0.5 * cRn; s2.sprime = p.shift_c + 0.5 * cUN;
         s2.scale = scale; s2.sgn = sgn;
         s2.nKf = 0; s2.nhm = 0; s2.ncR2 = 0; s2.nldg = 0; s2.nalpha = 0.0; s2.nsprime = 0.0;
+        s2.tab = tab2; s2.Rfp = Rfp2; s2.nKfp = 0;
+        s2.sm_slots = slots_dev + 256; s2.skew_cycles = (long long)((Kf2 + FBK - 1) / FBK) * SKEW_CYCLES_PER_KTILE;
         s2.tiles_r = (s2.Rf + FBR - 1) / FBR; s2.tiles_c = (s2.C + FBC - 1) / FBC;
         if (s2.tiles_r * s2.tiles_c > max_t2) max_t2 = s2.tiles_r * s2.tiles_c;
     }
@@ -414,14 +510,22 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
     LFD_CUDA_OK(e);
     const FoldDesc *df = (const FoldDesc *)workspace;
     const FStageDesc *ds = (const FStageDesc *)((char *)workspace + (size_t)count * sizeof(FoldDesc));
+    phase_table_kernel<<<dim3((max_tab + 255) / 256, 2 * count), 256, 0, stream>>>(ds);
+    LFD_CUDA_OK(cudaGetLastError());
     fold_kernel<<<dim3(max_rows, count), 256, 0, stream>>>(df);
     LFD_CUDA_OK(cudaGetLastError());
     mft_folded_kernel<true><<<dim3(max_t1, count), FTHREADS, FSMEM_BYTES, stream>>>(ds);
     LFD_CUDA_OK(cudaGetLastError());
     mft_folded_kernel<false><<<dim3(max_t2, count), FTHREADS, FSMEM_BYTES, stream>>>(ds + count);
     LFD_CUDA_OK(cudaGetLastError());
-    count_launch(3);
+    count_launch(4);
     return 0;
 }
 
 }  // namespace lfd
+
+#ifdef LFD_TILE_TIMING
+extern "C" int lfd_debug_tile_timing(long long *buf_dev) {
+    return (int)cudaMemcpyToSymbol(lfd::g_tile_timing, &buf_dev, sizeof(buf_dev));
+}
+#endif

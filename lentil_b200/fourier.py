@@ -41,6 +41,22 @@ def mft_flops(descs, count):
     return float(sum(8.0 * descs[i].M * descs[i].n * (descs[i].m + descs[i].N) for i in range(count)))
 
 
+def mft_flops_executed(descs, count):
+    """Real flops the DMMA pipe actually executes for a batch (unpadded): the folded variant runs
+    two real x complex GEMMs of ceil(M/2) x ceil(K/2) per stage, the direct one a complex x complex
+    GEMM of M x K."""
+    folded = _lib.lib().lfd_get_mft_variant() == 1
+    tot = 0.0
+    for i in range(count):
+        d = descs[i]
+        if folded:
+            h = lambda v: (v + 1) // 2
+            tot += 8.0 * d.n * h(d.M) * h(d.m) + 8.0 * d.M * h(d.N) * h(d.n)
+        else:
+            tot += 8.0 * d.M * d.n * (d.m + d.N)
+    return tot
+
+
 def run_mft(descs, count):
     """Launch a batch of planes on the current stream with a torch-owned workspace."""
     L = _lib.lib()
@@ -54,7 +70,7 @@ def run_mft(descs, count):
                "lfd_mft_c128_batched")
     if TIMERS is not None:
         e1.record()
-        TIMERS.append((e0, e1, mft_flops(descs, count)))
+        TIMERS.append((e0, e1, mft_flops(descs, count), mft_flops_executed(descs, count)))
     return ws
 
 
