@@ -149,6 +149,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    try:   # torchrun exports OMP_NUM_THREADS=1; the reference arm may use every host thread
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     amp, opd, wls, wts = make_inputs(WORKLOAD["nlam"])
     per_step = 4
     cpu_reference_psf(amp, opd, wls[:1], wts[:1])
@@ -293,7 +298,10 @@ def run_ours(args):
     achieved = mft_flops / (mft_ms * 1e-3) / 1e12 if mft_ms > 0 else None
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "mft_ncu_summary.json"))).get("dram_bytes_per_launch")
+        # ncu --set full capture (profiles/): DRAM bytes per plane per GEMM stage, scaled to one timed
+        # launch here (= both stages of every plane of the step on this rank)
+        per_stage = json.load(open(os.path.join(ROOT, "profiles", "mft_ncu_summary.json")))["dram_bytes_per_plane_stage"]
+        traffic = per_stage * 2 * w["nlam"]
     except Exception:
         pass
     executed = mft_exec / (mft_ms * 1e-3) / 1e12 if mft_ms > 0 else None
@@ -318,8 +326,13 @@ def run_ours(args):
     }
 
     # ---- CPU baseline (bounded sample of the same workload) -------------------------------------------
-    cpu_value, cpu_planes, cpu_s, kind = time_cpu(amp, opd, wls[:w["nlam"]], wts[:w["nlam"]], budget_s=12.0,
-                                                  max_planes=40)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
+    cpu_value, cpu_planes, cpu_s, kind = time_cpu(amp, opd, wls[:w["nlam"]], wts[:w["nlam"]],
+                                                  budget_s=12.0 if world == 1 else 3.0, max_planes=40)
     # parity spot check of this very run against the CPU reference (one wavelength)
     ref1, _ = cpu_reference_psf(amp, opd, wls[:1], wts[:1])
     got1 = lentil.propagate_dft_batch(pupil, wls[:1], w["du"], shape, oversample=w["oversample"], weights=wts[:1])

@@ -74,7 +74,8 @@ if __name__ == "__main__":
     mft = [d for d in F if "mft" in d["kernel"]]
     if mft:
         tr = sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in mft) / len(mft)
-        json.dump({"dram_bytes_per_launch": tr, "source": f"profiles/{tag}_mft_ncu.json",
+        json.dump({"dram_bytes_per_launch": tr, "planes_per_profiled_launch": 8,
+                   "dram_bytes_per_plane_stage": tr / 8, "source": f"profiles/{tag}_mft_ncu.json",
                    "note": "ncu --set full on scripts/ncu_target.py (8 planes 1001^2->1024^2 per launch)",
                    "tensor_pipe_active_pct": sum(d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0) for d in mft) / len(mft)},
                   open(os.path.join(ROOT, "profiles", "mft_ncu_summary.json"), "w"), indent=1)
