@@ -268,6 +268,20 @@ class Plane(_PlaneBase):
         _lib.check(rc, "lfd_pupil_prep")
         return ops, buf
 
+    def _phasors_into(self, buf, wavelengths, ops, opd_dev=None):
+        """K1 into rows of an existing (nlam, total) buffer, optionally with another OPD map
+        (a Monte-Carlo realisation) in place of the plane's own."""
+        lam = np.ascontiguousarray(wavelengths, dtype=np.float64).reshape(-1)
+        opd = ops['opd'] if opd_dev is None else opd_dev
+        rc = _lib.lib().lfd_pupil_prep(
+            ops['amp'].data_ptr(), opd.data_ptr(),
+            ops['mask'].data_ptr() if ops['mask'] is not None else None,
+            ops['shape'][0], ops['shape'][1], ops['segs'], ops['nseg'],
+            lam.ctypes.data_as(C.POINTER(C.c_double)), len(lam),
+            buf.data_ptr(), ops['total'], device.stream_ptr())
+        _lib.check(rc, "lfd_pupil_prep")
+        return buf
+
     @staticmethod
     def _segment_view(ops, buf_row, k):
         sg = ops['segs'][k]

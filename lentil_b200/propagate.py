@@ -141,24 +141,29 @@ def _shift_for(tilts, z, wavelength, du, oversample):
 
 
 def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, oversample=2,
-                        mask=None, weights=None, tilts=None, out=None, chunk_bytes=8 << 30,
+                        mask=None, weights=None, tilts=None, opds=None, out=None, chunk_bytes=8 << 30,
                         distributed=False, return_device=False):
-    """Polychromatic, multi-field-point PSF stack in one call.
+    """Polychromatic, multi-field-point, multi-realisation PSF stack in one call.
 
     Equivalent to the reference user loop (docs/user/performance.rst:44-49)::
 
-        for p, tilt in enumerate(tilts):
-            for wl, wt in zip(wavelengths, weights):
-                w = Wavefront(wl, tilt=tilt) * plane
-                w = propagate_dft(w, pixelscale, shape, prop_shape, oversample, mask)
-                img[p] = w.insert(img[p], wt)
+        for r, opd in enumerate(opds):                # optional Monte-Carlo WFE realisations
+            plane.opd = opd
+            for p, tilt in enumerate(tilts):          # optional field points
+                for wl, wt in zip(wavelengths, weights):
+                    w = Wavefront(wl, tilt=tilt) * plane
+                    w = propagate_dft(w, pixelscale, shape, prop_shape, oversample, mask)
+                    img[r, p] = w.insert(img[r, p], wt)
 
     plane : Pupil (or Plane with ptype pupil/image and a focal length on the wavefront side)
     wavelengths : (L,) metres;  weights : (L,) default 1
-    tilts : None (on-axis, returns (H, W)) or sequence of [rx, ry] field points (returns (P, H, W))
-    out : optional float64 device tensor to accumulate into (shape (P, H, W) or (H, W))
+    tilts : None (on-axis) or sequence of [rx, ry] field points -> axis of length P
+    opds : None (use plane.opd) or array (R, n, n) of OPD maps (host or device) -> axis of length R
+    out : optional float64 device tensor to accumulate into, shape ([R,] [P,] H, W)
     distributed : shard the wavelengths over torch.distributed ranks and all-reduce the stack
     return_device : return the device tensor instead of a numpy array
+
+    Returns ([R,] [P,] H, W): axes that were not requested are squeezed away.
 
     Host work is O(field points x segments) window planning plus numpy-vectorised descriptor
     tables (one row per plane); everything per-pixel runs in K1 / K2a / K3.
@@ -169,7 +174,6 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
     weights = np.ones(L) if weights is None else np.asarray(weights, dtype=float).reshape(-1)
     if len(weights) != L:
         raise ValueError('weights and wavelengths must have the same length')
-    squeeze = tilts is None
     points = [None] if tilts is None else [Tilt(x=t[0], y=t[1]) for t in tilts]
     P = len(points)
 
@@ -178,6 +182,13 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
     ops = plane._operands()
     if ops['scalar'] is not None:
         raise ValueError('propagate_dft_batch needs a plane with array amplitude or opd')
+    if opds is None:
+        R, opd_stack = 1, None
+    else:
+        opd_stack = opds if device.is_dev(opds) else device.to_dev(np.asarray(opds), dtype=np.float64)
+        if opd_stack.dim() != 3 or tuple(opd_stack.shape[1:]) != tuple(ops['shape']):
+            raise ValueError(f"opds must have shape (R, {ops['shape'][0]}, {ops['shape'][1]})")
+        R = int(opd_stack.shape[0])
 
     shape = np.broadcast_to(shape, (2,))
     prop_shape = np.asarray(shape) if prop_shape is None else np.broadcast_to(prop_shape, (2,))
@@ -190,8 +201,8 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
     z = getattr(plane, 'focal_length', None)
 
     my = shard_indices(L, distributed)
-    stack = out if out is not None else device.zeros_f64(P, H, W)
-    stack3 = stack.view(P, H, W)
+    stack = out if out is not None else device.zeros_f64(R * P, H, W)
+    stack3 = stack.view(R * P, H, W)
 
     nseg = ops['nseg']
     segs = ops['segs']
@@ -200,11 +211,12 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
              for p in range(P) for n in range(nseg)]
     # plain Tilt objects shift by the same number of pixels at every wavelength: plan once
     static = all(type(t) is Tilt for _, _, tl in pairs for t in tl)
-    # bytes per wavelength: phasors + (folded intermediates + output window) per field point
-    per_lam = 16 * ops['total'] + P * sum(
+    # bytes per wavefront (one realisation at one wavelength): phasors + per field point the folded
+    # intermediates and the output window
+    per_wf = 16 * ops['total'] + P * sum(
         16 * (2 * int(segs[n].w) * int(prop_shape_out[0]) + int(prop_shape_out[0]) * int(prop_shape_out[1]))
         for n in range(nseg))
-    step = max(1, int(chunk_bytes // max(per_lam, 1)))
+    step = max(1, int(chunk_bytes // max(per_wf, 1)))
 
     seg_off = np.array([segs[n].out_offset for n in range(nseg)], dtype=np.int64)
     seg_h = np.array([segs[n].h for n in range(nseg)], dtype=np.int64)
@@ -212,36 +224,44 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
     offs = np.array(ops['offsets'], dtype=float).reshape(nseg, 2)
     alpha_num = (dx[0] * du[0], dx[1] * du[1])
 
-    for c0 in range(0, len(my), step):
-        idx = my[c0:c0 + step]
-        lam = wavelengths[idx]
-        nl = len(lam)
-        _, phasors = plane._phasors(lam, ops)                               # K1
-        # ---- window planning: rows (li, p, n) -> window shape / offset / dft shift -----------------
+    # wavefronts of this rank: realisation-major, wavelength-minor
+    wf_r = np.repeat(np.arange(R, dtype=np.int64), len(my))
+    wf_l = np.tile(np.asarray(my, dtype=np.int64), R)
+
+    for c0 in range(0, len(wf_r), step):
+        cr, cl = wf_r[c0:c0 + step], wf_l[c0:c0 + step]
+        lam = wavelengths[cl]
+        nw = len(lam)
+        phasors = device.empty_c128(nw, ops['total'])
+        for r in np.unique(cr):                                            # K1, one launch per realisation
+            sel = np.flatnonzero(cr == r)
+            plane._phasors_into(phasors[int(sel[0]):int(sel[-1]) + 1], lam[sel], ops,
+                                None if opd_stack is None else opd_stack[int(r)])
+        # ---- window planning: rows (wavefront, p, n) -> window shape / offset / dft shift ----------
         if static:
             plans = [plan_window(_shift_for(tl, z, lam[0], du, oversample), prop_shape_out, out_extent)
                      for _, _, tl in pairs]
             keep = [k for k, pl in enumerate(plans) if pl is not None]
-            jp = np.tile(np.array([pairs[k][0] for k in keep], dtype=np.int64), nl)
-            jn = np.tile(np.array([pairs[k][1] for k in keep], dtype=np.int64), nl)
-            jl = np.repeat(np.arange(nl, dtype=np.int64), len(keep))
-            jshape = np.tile(np.array([plans[k][0] for k in keep], dtype=np.int64).reshape(-1, 2), (nl, 1))
-            jshift = np.tile(np.array([plans[k][1] for k in keep], dtype=np.int64).reshape(-1, 2), (nl, 1))
-            jdft = np.tile(np.array([plans[k][2] for k in keep], dtype=float).reshape(-1, 2), (nl, 1))
+            jp = np.tile(np.array([pairs[k][0] for k in keep], dtype=np.int64), nw)
+            jn = np.tile(np.array([pairs[k][1] for k in keep], dtype=np.int64), nw)
+            jw = np.repeat(np.arange(nw, dtype=np.int64), len(keep))
+            jshape = np.tile(np.array([plans[k][0] for k in keep], dtype=np.int64).reshape(-1, 2), (nw, 1))
+            jshift = np.tile(np.array([plans[k][1] for k in keep], dtype=np.int64).reshape(-1, 2), (nw, 1))
+            jdft = np.tile(np.array([plans[k][2] for k in keep], dtype=float).reshape(-1, 2), (nw, 1))
         else:
             rows = []
-            for li, wl in enumerate(lam):
+            for wi, wl in enumerate(lam):
                 for p, n, tl in pairs:
                     pl = plan_window(_shift_for(tl, z, wl, du, oversample), prop_shape_out, out_extent)
                     if pl is not None:
-                        rows.append((li, p, n, pl))
-            jl = np.array([r[0] for r in rows], dtype=np.int64)
+                        rows.append((wi, p, n, pl))
+            jw = np.array([r[0] for r in rows], dtype=np.int64)
             jp = np.array([r[1] for r in rows], dtype=np.int64)
             jn = np.array([r[2] for r in rows], dtype=np.int64)
             jshape = np.array([r[3][0] for r in rows], dtype=np.int64).reshape(-1, 2)
             jshift = np.array([r[3][1] for r in rows], dtype=np.int64).reshape(-1, 2)
             jdft = np.array([r[3][2] for r in rows], dtype=float).reshape(-1, 2)
-        nj = len(jl)
+        nj = len(jw)
         if nj == 0:
             continue
         sizes = jshape[:, 0] * jshape[:, 1]
@@ -249,35 +269,45 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
         buf = device.empty_c128(int(sizes.sum()))
         # ---- K2a descriptors, one row per plane -------------------------------------------------
         D = np.zeros(nj, dtype=np.dtype(_lib.MftDesc))
-        D['f'] = phasors.data_ptr() + 16 * (jl * ops['total'] + seg_off[jn])
+        D['f'] = phasors.data_ptr() + 16 * (jw * ops['total'] + seg_off[jn])
         D['ldf'] = seg_w[jn]
         D['out'] = buf.data_ptr() + 16 * pos
         D['ldo'] = jshape[:, 1]
         D['m'], D['n'] = seg_h[jn], seg_w[jn]
         D['M'], D['N'] = jshape[:, 0], jshape[:, 1]
-        D['alpha_r'] = alpha_num[0] / (lam[jl] * z * oversample)
-        D['alpha_c'] = alpha_num[1] / (lam[jl] * z * oversample)
+        D['alpha_r'] = alpha_num[0] / (lam[jw] * z * oversample)
+        D['alpha_c'] = alpha_num[1] / (lam[jw] * z * oversample)
         D['shift_r'], D['shift_c'] = jdft[:, 0], jdft[:, 1]
         D['off_r'], D['off_c'] = offs[jn, 0], offs[jn, 1]
         D['unitary'] = 1
-        _fourier.run_mft(D.ctypes.data_as(C.POINTER(_lib.MftDesc)), nj)      # K2a
-        # ---- K3: per field point, groups = wavelengths ---------------------------------------------
+        for b0 in range(0, nj, _MAX_PLANES_PER_LAUNCH):                      # K2a
+            nb = min(_MAX_PLANES_PER_LAUNCH, nj - b0)
+            _fourier.run_mft(D[b0:b0 + nb].ctypes.data_as(C.POINTER(_lib.MftDesc)), nb)
+        # ---- K3: per output image (realisation, field point); groups = wavefronts --------------------
         Wn = np.zeros(nj, dtype=np.dtype(_lib.Window))
         Wn['E'], Wn['ld'] = D['out'], jshape[:, 1]
         Wn['h'], Wn['w'] = jshape[:, 0], jshape[:, 1]
         Wn['r0'] = H // 2 - jshape[:, 0] // 2 + jshift[:, 0]      # lentil/field.py:267-268
         Wn['c0'] = W // 2 - jshape[:, 1] // 2 + jshift[:, 1]
-        Wn['group'] = jl
-        Wn['weight'] = weights[idx][jl]
-        for p in range(P):
-            sel = Wn[jp == p] if P > 1 else Wn
+        Wn['group'] = jw
+        Wn['weight'] = weights[cl][jw]
+        img = cr[jw] * P + jp
+        for im in np.unique(img):
+            sel = Wn[img == im] if (R * P) > 1 else Wn
             if len(sel):
-                _field.accumulate_windows(np.ascontiguousarray(sel), stack3[p])
+                _field.accumulate_windows(np.ascontiguousarray(sel), stack3[int(im)])
 
     if distributed:
         reduce_stack(stack)
-    result = stack3[0] if squeeze else stack3
-    return result if return_device else device.to_host(result)
+    result = stack3.view(R, P, H, W)
+    if tilts is None:
+        result = result[:, 0]
+    if opds is None:
+        result = result[0]
+    return result if return_device else device.to_host(result.contiguous())
+
+
+_MAX_PLANES_PER_LAUNCH = 16384      # lfd_mft_c128_batched takes at most 32767 planes per call
 
 
 def shard_indices(L, distributed=False, rank=None, world=None):

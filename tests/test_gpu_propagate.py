@@ -290,3 +290,29 @@ def test_tilt_plane_and_product_of_planes():
     f1 = oc.plane_multiply(f0, stop.amplitude, stop.opd, None, 650e-9)
     assert tuple(int(v) for v in w2.data[0].offset) == tuple(f1[0]["offset"])
     assert peak_err(w2.data[0].data, f1[0]["data"]) <= 1e-14
+
+
+def test_monte_carlo_opd_stack_against_oracle():
+    # BASELINE config 4 structure at small scale: WFE realisations x wavelengths (x focus diversity folded
+    # into the realisation axis) -> one polychromatic PSF per realisation
+    rng = np.random.default_rng(11)
+    mask = synth.circle((96, 96), 45)
+    amp = synth.normalize_power(mask)
+    opds = np.stack([synth.zernike_opd(mask, rng.normal(size=12) * 20e-9, first=4) for _ in range(5)])
+    dx, z, du = 1 / 90, 20.0, 5e-6
+    wls = np.linspace(600e-9, 700e-9, 4)
+    wts = np.array([0.1, 0.4, 0.3, 0.2])
+    p = lentil.Pupil(amplitude=amp, opd=np.zeros((96, 96)), pixelscale=dx, focal_length=z)
+    stack = lentil.propagate_dft_batch(p, wls, du, (48, 48), oversample=2, weights=wts, opds=opds)
+    assert stack.shape == (5, 96, 96)
+    for r in range(5):
+        ref = oc.psf(amp, opds[r], None, wls, wts, (dx, dx), z, du, (48, 48), None, 2)
+        assert peak_err(stack[r], ref) <= TOL64
+    # realisations x field points, tiny chunks
+    tilts = [[0.0, 0.0], [6e-6, -4e-6]]
+    s2 = lentil.propagate_dft_batch(p, wls, du, (48, 48), oversample=2, weights=wts, opds=opds[:2], tilts=tilts,
+                                    chunk_bytes=1)
+    assert s2.shape == (2, 2, 96, 96)
+    assert peak_err(s2[:, 0], stack[:2]) <= 1e-13
+    ref = oc.psf(amp, opds[1], None, wls, wts, (dx, dx), z, du, (48, 48), None, 2, wf_tilt=tilts[1])
+    assert peak_err(s2[1, 1], ref) <= TOL64
