@@ -81,6 +81,15 @@ int lfd_mft_c128_batched(const lfd_mft_desc *descs_host, int count,
 int lfd_mft_c128(const lfd_mft_desc *desc_host, void *workspace_dev, size_t workspace_bytes,
                  void *stream);
 
+/* ---- K2b: the same transform with complex64 in/out, 3xTF32 split precision on tcgen05 -------
+ * Same descriptor, but `f` and `out` are complex64 (interleaved floats).  Every real product is
+ * evaluated as hi*hi + hi*lo + lo*hi in TF32 with fp32 accumulation in TMEM; peak-normalised error
+ * ~1e-6 (gate 1e-5).  lentil itself has no complex64 mode (Field casts to complex128,
+ * lentil/field.py:35): this is the optional fast path BASELINE.json's north star names. */
+size_t lfd_mft_c64x3_workspace_bytes(const lfd_mft_desc *descs_host, int count);
+int lfd_mft_c64x3_batched(const lfd_mft_desc *descs_host, int count,
+                          void *workspace_dev, size_t workspace_bytes, void *stream);
+
 /* ---- K1: pupil prep ------------------------------------------------------------------
  * For each wavelength w and segment s:  out_{w,s}[r,c] = amp[r,c] * mask_s[r,c] *
  * exp(+2 pi i opd[r,c] / lambda_w)  over the segment's bounding box.

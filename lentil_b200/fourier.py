@@ -57,9 +57,16 @@ def mft_flops_executed(descs, count):
     return tot
 
 
-def run_mft(descs, count):
-    """Launch a batch of planes on the current stream with a torch-owned workspace."""
+def run_mft(descs, count, precision='c128'):
+    """Launch a batch of planes on the current stream with a torch-owned workspace.
+    precision 'c128': K2a (FP64 DMMA); 'c64': K2b (complex64 arrays, 3xTF32 on tcgen05)."""
     L = _lib.lib()
+    if precision == 'c64':
+        need = L.lfd_mft_c64x3_workspace_bytes(descs, count)
+        ws = device.empty_bytes(need)
+        _lib.check(L.lfd_mft_c64x3_batched(descs, count, ws.data_ptr(), need, device.stream_ptr()),
+                   "lfd_mft_c64x3_batched")
+        return ws
     need = L.lfd_mft_workspace_bytes(descs, count)
     ws = device.empty_bytes(need)
     if TIMERS is not None:
@@ -77,13 +84,15 @@ def run_mft(descs, count):
 def dft2_dev(f_dev, alpha, shape=None, shift=(0, 0), offset=(0, 0), unitary=True, inverse=False,
              out=None):
     """dft2 on device arrays; returns a complex128 device tensor (no host transfer)."""
+    import torch
     m, n = int(f_dev.shape[0]), int(f_dev.shape[1])
     M, N = (m, n) if shape is None else (int(v) for v in _pair(shape))
+    c64 = f_dev.dtype == torch.complex64
     if out is None:
-        out = device.empty_c128(M, N)
+        out = torch.empty(M, N, dtype=f_dev.dtype, device=f_dev.device)
     descs = (_lib.MftDesc * 1)()
     mft_descriptor(descs[0], f_dev, out, alpha, shift, offset, unitary, inverse)
-    run_mft(descs, 1)
+    run_mft(descs, 1, 'c64' if c64 else 'c128')
     return out
 
 
@@ -114,3 +123,16 @@ def idft2(F, alpha, shape=None, shift=(0, 0), unitary=True, out=None):
     """Inverse transform, conj(dft2(conj F)) / F.size (lentil/fourier.py:124-198): the
     conjugations fold into the twiddle sign, the division into the output scale."""
     return _transform(F, alpha, shape, shift, (0, 0), unitary, out, inverse=True)
+
+
+def dft2_c64(f, alpha, shape=None, shift=(0, 0), offset=(0, 0), unitary=True):
+    """dft2 with complex64 input/output on the 3xTF32 tensor-core path (K2b).  Not part of the
+    reference surface (lentil is complex128 throughout): the optional fast mode of the north star,
+    peak-normalised error ~1e-6."""
+    f_dev = device.to_dev(np.asarray(f), dtype=np.complex64)
+    return device.to_host(dft2_dev(f_dev, alpha, shape, shift, offset, unitary, inverse=False))
+
+
+def idft2_c64(F, alpha, shape=None, shift=(0, 0), unitary=True):
+    f_dev = device.to_dev(np.asarray(F), dtype=np.complex64)
+    return device.to_host(dft2_dev(f_dev, alpha, shape, shift, (0, 0), unitary, inverse=True))
