@@ -16,17 +16,19 @@
 // Per CTA (one tile = 256 folded rows x 32 complex columns, K looped in blocks of 8):
 //   warp 0        : TMEM alloc; one lane issues 12 UMMAs (128x64x8) per k-block and commits
 //                   them to the stage's `empty` mbarrier
-//   warps 1..8    : one thread per folded row.  Each k-block they (a) cp.async the data operand
-//                   (ge/go, hi/lo: 8 KB) two blocks ahead, (b) generate the row's 8 cos/sin
+//   warps 1..8    : one thread per folded row.  Each k-block they generate the row's 8 cos/sin
 //                   twiddles — an fp64 twiddle carried across k-blocks by one complex rotation,
 //                   times 8 fp32 in-block factors — split them to tf32 hi/lo and store them in the
-//                   UMMA canonical K-major (no-swizzle) layout, (c) fence.proxy.async and arrive on
-//                   the stage's `full` mbarrier.  After the K loop the same warps are the epilogue:
+//                   UMMA canonical K-major (no-swizzle) layout, then fence.proxy.async and arrive on
+//                   the stage's `fullA` mbarrier.  After the K loop the same warps are the epilogue:
 //                   tcgen05.ld their TMEM lane, unfold (+U', -U'), apply the post phase and either
 //                   write complex64 output or the hi/lo-split, column-folded operand of the next stage.
-// Data operand in HBM: four planes (ge_hi, ge_lo, go_hi, go_lo), each [real column n][K] with K
-// contiguous — produced by fold_split_kernel (stage 1) and by the stage-1 epilogue (stage 2), so
-// a thread's 16 consecutive K values form one 64-byte run.
+//   warp 9        : one lane moves the data operand of a k-block (ge/go, hi/lo: 8 KB) with a single
+//                   cp.async.bulk into a 12-slot ring, signalling the slot's `fullB` mbarrier by tx count
+// Data operand in HBM: PRE-BLOCKED in the UMMA canonical layout.  Block (column tile, k-block) is
+// 8 KB = 4 planes (ge_hi, ge_lo, go_hi, go_lo) x [n/8][k/4][n%8][k%4] floats for 64 real columns
+// x 8 K, so that one contiguous bulk copy lands it ready for the tensor core.  fold_split_kernel
+// (stage 1) and the stage-1 epilogue (stage 2) write that layout directly.
 #include "lfd_common.cuh"
 
 namespace lfd {
@@ -37,20 +39,25 @@ constexpr int TN = 32;        // complex columns per CTA = 64 real columns (UMMA
 constexpr int NR = 2 * TN;    // UMMA N
 constexpr int HALF = TN / 2;  // FOLD_OUT: folded columns per tile (HALF columns j+ and their HALF mirrors)
 constexpr int KB = 8;         // folded K per k-block (UMMA K for tf32)
-constexpr int NSTAGE = 4;
-constexpr int PREFETCH = 2;   // k-blocks of data operand in flight per thread
+constexpr int NA = 3;         // twiddle (A operand) stages, 32 KB each
+constexpr int NB = 12;        // data (B operand) slots, 8 KB each: a deeper ring, because the data comes from
+                              // L2/HBM (~2000 cycles) while a k-block of MMAs lasts ~400
 constexpr int A_ARR = 256 * KB * 4;            // one twiddle plane: 8 KB
 constexpr int B_ARR = NR * KB * 4;             // one data plane: 2 KB
 constexpr int A_BYTES = 4 * A_ARR, B_BYTES = 4 * B_ARR;
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES; // 40 KB
+constexpr int B_RING = NA * A_BYTES;           // byte offset of the data ring behind the twiddle stages
 constexpr int NGEN = 256;                      // generator / epilogue threads
-constexpr int NTHREADS = 32 + NGEN;
-constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + 1024;
-constexpr int LBO = 128, SBO = 256;            // canonical K-major, SWIZZLE_NONE (see scripts/micro/umma_test.cu)
+constexpr int NTHREADS = 32 + NGEN + 32;         // MMA warp + generators + bulk-copy producer warp
+constexpr size_t SMEM_BYTES = (size_t)NA * A_BYTES + (size_t)NB * B_BYTES + 1024;
+// Operand tiles are K-major with 32-byte rows (8 tf32 = one UMMA K) in the SWIZZLE_32B canonical layout:
+// row r of a tile sits at (r/8)*256 + (r%8)*32 and its two 16-byte K chunks are swapped when (r%8) >= 4
+// (address bit 4 ^= bit 7), which is what keeps the tensor core's operand reads bank-conflict free.
+constexpr int SBO = 256;
+__host__ __device__ __forceinline__ int tile_off(int r, int kc) { return (r >> 3) * SBO + (r & 7) * 32 + ((kc ^ ((r >> 2) & 1)) << 4); }
 
 struct CStage {
-    const float *B;          // data operand: 4 planes of [Npad][Kpad] floats
-    long long plane;         // floats per plane = Npad * Kpad
+    const unsigned char *B;  // pre-blocked data operand, (Npad / 64) x (Kpad / 8) blocks of 8 KB
+    long long plane;         // unused
     int Kf, Kpad, C, Npad;
     int Rf, M, hM, cR2, cU2, Rfp;
     int tiles_r, tiles_c;
@@ -61,7 +68,7 @@ struct CStage {
     const float2 *tabf;
     // outputs
     float2 *out; long long ldo;            // final stage: complex64 M x N (row-major), written transposed
-    float *nB; long long nplane;           // FOLD_OUT: next stage's data operand
+    unsigned char *nB; long long nplane;   // FOLD_OUT: next stage's pre-blocked data operand
     int nKf, nKpad, nhm, ncR2, nKfp, pad_;
     double alpha, oprime, sprime, scale, nalpha, nsprime;
 };
@@ -83,12 +90,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
     }
 }
 
+// one lane of a converged warp (the compiler can then keep tcgen05 operands in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((LBO >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)1 << 16;                             // LBO: unused for swizzled K-major layouts
     d |= (uint64_t)((SBO >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;    // descriptor version 1 (sm_100); SWIZZLE_NONE, base offset 0
+    d |= (uint64_t)1 << 46;                             // descriptor version 1 (sm_100)
+    d |= (uint64_t)6 << 61;                             // layout type SWIZZLE_32B
     return d;
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
@@ -113,6 +128,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// byte offset of element (plane a, real column n, K index r) inside a pre-blocked data operand with nkb k-blocks
+__host__ __device__ __forceinline__ long long bop_offset(int a, int n, int r, int nkb) {
+    return ((long long)(n / NR) * nkb + r / KB) * B_BYTES + a * B_ARR + tile_off(n % NR, (r % KB) / 4) + (r % 4) * 4;
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
@@ -148,7 +172,7 @@ phase_table_c64_kernel(const CStage *__restrict__ descs) {
 // ---- fold + split + transpose: complex64 f (K x C) -> stage-1 data operand ----------------------------
 struct FoldSplit {
     const float2 *D; long long ldd;
-    float *B; long long plane;       // 4 planes [Npad][Kpad]
+    unsigned char *B; long long plane;  // pre-blocked data operand of stage 1
     int K, C, Kf, Kpad, hm, cR2;
     int permute;                     // 1: columns arranged as HALF (j+) + HALF (j-) per TN-slot tile for FOLD_OUT
     int nhm, ncR2, nKf, slots;       // slots = Npad / 2
@@ -200,30 +224,44 @@ fold_split_kernel(const FoldSplit *__restrict__ descs) {
         tile[0][rr][tx] = ger; tile[1][rr][tx] = gei; tile[2][rr][tx] = gor; tile[3][rr][tx] = goi;
     }
     __syncthreads();
-    // transposed, split write: for each slot (ty-strided) 32 consecutive K values (tx)
+    // this CUDA block owns one column tile (64 real columns) x 4 k-blocks = 4 x 8 KB of the pre-blocked
+    // operand; consecutive threads write consecutive 16-byte chunks (4 K values of one real column)
+    const int tileN = s0 / 32, nkb = d.Kpad / KB;
 #pragma unroll
-    for (int ss = ty; ss < 32; ss += 8) {
-        const int sl = s0 + ss;
-        if (sl >= d.slots || r0 + tx >= d.Kpad) continue;
+    for (int it = 0; it < 8; ++it) {
+        const int c = threadIdx.x + 256 * it;          // 0 .. 2047
+        const int kbl = c >> 9, a = (c >> 7) & 3, q = c & 127;
+        const int n = q >> 1, kc = (q & 1) ^ ((n >> 2) & 1);       // physical chunk q & 1 holds logical K chunk kc
+        const int sl = n >> 1, part = n & 1;
+        float v[4];
 #pragma unroll
-        for (int part = 0; part < 2; ++part) {
-            const float ge = tile[part][tx][ss], go = tile[2 + part][tx][ss];
-            const float geh = tf32_hi(ge), goh = tf32_hi(go);
-            const long long o = ((long long)(2 * sl + part)) * d.Kpad + r0 + tx;
-            d.B[o] = geh;
-            d.B[d.plane + o] = ge - geh;
-            d.B[2 * d.plane + o] = goh;
-            d.B[3 * d.plane + o] = go - goh;
+        for (int jj = 0; jj < 4; ++jj) {
+            const float x = tile[(a >> 1) * 2 + part][kbl * 8 + kc * 4 + jj][sl];
+            const float h = tf32_hi(x);
+            v[jj] = (a & 1) ? (x - h) : h;
         }
+        unsigned char *dst = d.B + ((long long)tileN * nkb + (r0 / KB + kbl)) * B_BYTES + a * B_ARR + q * 16;
+        *(float4 *)dst = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
+
+#ifdef LFD_TILE_TIMING
+__device__ long long *g_c64_timing = nullptr;   // per CTA: [mma wait fullA, mma wait fullB, mma issue, gen wait emptyA, gen work, gen fence+arrive, prod wait, total]
+#define TT_DECL long long tt_a = 0, tt_b = 0, tt_c = 0, tt_t0 = clock64(), tt_x;
+#define TT_BEGIN tt_x = clock64();
+#define TT_ADD(v) { long long n__ = clock64(); v += n__ - tt_x; tt_x = n__; }
+#else
+#define TT_DECL
+#define TT_BEGIN
+#define TT_ADD(v)
+#endif
 
 // ---- the tcgen05 stage kernel ------------------------------------------------------------------------
 template <bool FOLD_OUT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 mft_c64_kernel(const CStage *__restrict__ descs) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], tmem_full_bar;
+    __shared__ __align__(8) uint64_t fullA_bar[NA], emptyA_bar[NA], fullB_bar[NB], emptyB_bar[NB], tmem_full_bar;
     __shared__ uint32_t tmem_base_s;
 
     const CStage d = descs[blockIdx.y];
@@ -231,14 +269,14 @@ mft_c64_kernel(const CStage *__restrict__ descs) {
     if (tile >= d.tiles_r * d.tiles_c) return;
     const int tr = tile % d.tiles_r, tc = tile / d.tiles_r;
     const int r_base = tr * TM;
-    const int n_base = tc * NR;                     // first real column (row of the data planes) of this tile
 
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nkb = d.Kpad / KB;
 
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], NGEN / 32); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < NA; ++s) { mbar_init(&fullA_bar[s], NGEN / 32); mbar_init(&emptyA_bar[s], 1); }
+        for (int s = 0; s < NB; ++s) { mbar_init(&fullB_bar[s], 1); mbar_init(&emptyB_bar[s], 1); }
         mbar_init(&tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
@@ -252,15 +290,22 @@ mft_c64_kernel(const CStage *__restrict__ descs) {
     const uint32_t tmem = tmem_base_s;
 
     if (warp == 0) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer: the warp stays converged, one elected lane issues =================
+        {
+            TT_DECL
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NR >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % NSTAGE;
-                mbar_wait(&full_bar[s], (kb / NSTAGE) & 1);
+                const int s = kb % NA;
+                TT_BEGIN
+                mbar_wait(&fullA_bar[s], (kb / NA) & 1);
+                TT_ADD(tt_a)
+                mbar_wait(&fullB_bar[kb % NB], (kb / NB) & 1);
+                TT_ADD(tt_b)
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES), sb = sa + A_BYTES;
+                const uint32_t sa = smem_u32(smem + (size_t)s * A_BYTES);
+                const uint32_t sb = smem_u32(smem + B_RING + (size_t)(kb % NB) * B_BYTES);
                 const uint32_t acc = kb > 0 ? 1u : 0u;
+                if (elect_one()) {
 #pragma unroll
                 for (int rt = 0; rt < 2; ++rt) {
                     const uint32_t ro = rt * 4096;                       // rows 128..255 of each twiddle plane
@@ -277,12 +322,34 @@ mft_c64_kernel(const CStage *__restrict__ descs) {
                     umma_tf32(t0 + 3 * NR, sh, ol, idesc, acc);      // B_corr += sin_hi * go_lo
                     umma_tf32(t0 + 3 * NR, sl, oh, idesc, 1u);       //         + sin_lo * go_hi
                 }
-                umma_commit(&empty_bar[s]);                 // frees the stage when these MMAs retire
+                umma_commit(&emptyA_bar[s]);                // frees the twiddle stage and the data slot
+                umma_commit(&emptyB_bar[kb % NB]);          // when these MMAs retire
+                }
+                __syncwarp();
+                TT_ADD(tt_c)
             }
-            umma_commit(&tmem_full_bar);
+            if (elect_one()) umma_commit(&tmem_full_bar);
+            __syncwarp();
+#ifdef LFD_TILE_TIMING
+            if (g_c64_timing && lane == 0) { long long *o = g_c64_timing + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8; o[0] = tt_a; o[1] = tt_b; o[2] = tt_c; o[7] = clock64() - tt_t0; }
+#endif
+        }
+    } else if (warp == 9) {
+        // ================= data-operand producer: one bulk copy per k-block =================
+        if (lane == 0) {
+            const unsigned char *src = d.B + (long long)tc * nkb * B_BYTES;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int sl = kb % NB;
+                if (kb >= NB) mbar_wait(&emptyB_bar[sl], ((kb / NB) - 1) & 1);
+                const uint32_t bar = smem_u32(&fullB_bar[sl]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)B_BYTES) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(smem + B_RING + (size_t)sl * B_BYTES)), "l"(src + (long long)kb * B_BYTES),
+                               "r"((uint32_t)B_BYTES), "r"(bar) : "memory");
+            }
         }
     } else {
-        // ================= generators / loaders =================
+        // ================= twiddle generators =================
         const int g = tid - 32;                             // 0..255 = folded row within the tile
         const int u = r_base + g;
         double Wc, Ws, Rc, Rs;
@@ -293,40 +360,15 @@ mft_c64_kernel(const CStage *__restrict__ descs) {
 #pragma unroll
             for (int j = 0; j < KB; ++j) S[j] = d.tabf[(size_t)u * KB + j];
         }
-        // this thread's 2 data chunks (16 B) per k-block: (n, kc) = ((g % 128) / 2, g % 2), planes a0 and a0 + 1
-        // with a0 = 2 * (g / 128)
-        const int n = (g & 127) >> 1, kc = g & 1, a0 = (g >> 7) * 2;
-        const float *bsrc = d.B + (long long)(n_base + n) * d.Kpad + kc * 4;
-        const uint32_t bdst = A_BYTES + (n >> 3) * SBO + kc * LBO + (n & 7) * 16;
-        const uint32_t adst = (g >> 3) * SBO + (g & 7) * 16;
-
-        auto issue_loads = [&](int kb) {
-            const uint32_t sbase = smem_u32(smem + (size_t)(kb % NSTAGE) * STAGE_BYTES) + bdst;
-#pragma unroll
-            for (int a = a0; a < a0 + 2; ++a) {
-                const float *src = bsrc + a * d.plane + (long long)kb * KB;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + a * B_ARR), "l"(src));
-            }
-        };
-        // prologue: first PREFETCH k-blocks (stages are free)
-#pragma unroll
-        for (int p = 0; p < PREFETCH; ++p) {
-            if (p < nkb) issue_loads(p);
-            cp_async_commit();
-        }
+        const uint32_t adst = (g >> 3) * SBO + (g & 7) * 32;    // row g of a 256-row twiddle plane
+        const uint32_t swz = ((g >> 2) & 1) << 4;
+        TT_DECL
         for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % NSTAGE;
-            // loads for kb + PREFETCH need that stage to be free
-            {
-                const int nk = kb + PREFETCH;
-                if (nk < nkb) {
-                    if (nk >= NSTAGE) mbar_wait(&empty_bar[nk % NSTAGE], ((nk / NSTAGE) - 1) & 1);
-                    issue_loads(nk);
-                }
-                cp_async_commit();
-            }
-            // stage s itself must be free before the twiddles are written (implied for kb < PREFETCH + ...: wait anyway)
-            if (kb >= NSTAGE) mbar_wait(&empty_bar[s], ((kb / NSTAGE) - 1) & 1);
+            const int s = kb % NA;
+            TT_BEGIN
+            // the twiddle stage must be free before it is overwritten
+            if (kb >= NA) mbar_wait(&emptyA_bar[s], ((kb / NA) - 1) & 1);
+            TT_ADD(tt_a)
             // twiddles of this row for the 8 K of the block
             {
                 const float wc = (float)Wc, ws = (float)Ws;
@@ -337,23 +379,27 @@ mft_c64_kernel(const CStage *__restrict__ descs) {
                     ch[j] = tf32_hi(c); cl[j] = c - ch[j];
                     sh[j] = tf32_hi(sn); sl[j] = sn - sh[j];
                 }
-                unsigned char *sa = smem + (size_t)s * STAGE_BYTES + adst;
+                const uint32_t sa = smem_u32(smem + (size_t)s * A_BYTES) + adst;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    *(float4 *)(sa + 0 * A_ARR + h * LBO) = make_float4(ch[4 * h], ch[4 * h + 1], ch[4 * h + 2], ch[4 * h + 3]);
-                    *(float4 *)(sa + 1 * A_ARR + h * LBO) = make_float4(cl[4 * h], cl[4 * h + 1], cl[4 * h + 2], cl[4 * h + 3]);
-                    *(float4 *)(sa + 2 * A_ARR + h * LBO) = make_float4(sh[4 * h], sh[4 * h + 1], sh[4 * h + 2], sh[4 * h + 3]);
-                    *(float4 *)(sa + 3 * A_ARR + h * LBO) = make_float4(sl[4 * h], sl[4 * h + 1], sl[4 * h + 2], sl[4 * h + 3]);
+                    const uint32_t o = sa + ((h << 4) ^ swz);
+                    st_shared_v4(o + 0 * A_ARR, ch[4 * h], ch[4 * h + 1], ch[4 * h + 2], ch[4 * h + 3]);
+                    st_shared_v4(o + 1 * A_ARR, cl[4 * h], cl[4 * h + 1], cl[4 * h + 2], cl[4 * h + 3]);
+                    st_shared_v4(o + 2 * A_ARR, sh[4 * h], sh[4 * h + 1], sh[4 * h + 2], sh[4 * h + 3]);
+                    st_shared_v4(o + 3 * A_ARR, sl[4 * h], sl[4 * h + 1], sl[4 * h + 2], sl[4 * h + 3]);
                 }
                 const double nc = Wc * Rc - Ws * Rs, ns = Wc * Rs + Ws * Rc;
                 Wc = nc; Ws = ns;
             }
-            cp_async_wait<PREFETCH>();                       // this block's data has landed
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            TT_ADD(tt_b)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy STS -> visible to the MMA
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full_bar[s]);
+            if (lane == 0) mbar_arrive(&fullA_bar[s]);
+            TT_ADD(tt_c)
         }
-        cp_async_wait<0>();
+#ifdef LFD_TILE_TIMING
+        if (g_c64_timing && g == 0) { long long *o = g_c64_timing + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8; o[3] = tt_a; o[4] = tt_b; o[5] = tt_c; }
+#endif
 
         // ================= epilogue =================
         mbar_wait(&tmem_full_bar, 0);
@@ -459,7 +505,7 @@ mft_c64_kernel(const CStage *__restrict__ descs) {
                             for (int a4 = 0; a4 < 4; ++a4)
 #pragma unroll
                                 for (int part = 0; part < 2; ++part) {
-                                    float *dst = d.nB + a4 * d.nplane + (long long)(2 * k + part) * d.nKpad + r2_0 + 4 * v;
+                                    unsigned char *dst = d.nB + bop_offset(a4, 2 * k + part, r2_0 + 4 * v, d.nKpad / KB);
                                     *(float4 *)dst = make_float4(o[a4][part][0], o[a4][part][1], o[a4][part][2], o[a4][part][3]);
                                 }
                         }
@@ -533,8 +579,8 @@ int launch_mft_c64(const lfd_mft_desc *descs, int count, void *workspace, size_t
             LFD_REQUIRE(false, "lfd_mft_c64x3_batched: plane %d has invalid shape/ld/pointers", i);
         }
         const Geo g = geo(p);
-        float *B1 = (float *)(ws + off); off += al((size_t)4 * g.Npad1 * g.Kpad1 * sizeof(float));
-        float *B2 = (float *)(ws + off);
+        unsigned char *B1 = (unsigned char *)(ws + off); off += al((size_t)4 * g.Npad1 * g.Kpad1 * sizeof(float));
+        unsigned char *B2 = (unsigned char *)(ws + off);
         const size_t b2_bytes = al((size_t)4 * g.Npad2 * g.Kpad2 * sizeof(float));
         if (!b2_begin) b2_begin = (char *)B2;
         off += b2_bytes;
@@ -612,3 +658,9 @@ extern "C" int lfd_mft_c64x3_batched(const lfd_mft_desc *descs, int count, void 
                                      size_t workspace_bytes, void *stream) {
     return lfd::c64::launch_mft_c64(descs, count, workspace, workspace_bytes, (cudaStream_t)stream);
 }
+
+#ifdef LFD_TILE_TIMING
+extern "C" int lfd_debug_c64_timing(long long *buf_dev) {
+    return (int)cudaMemcpyToSymbol(lfd::c64::g_c64_timing, &buf_dev, sizeof(buf_dev));
+}
+#endif
