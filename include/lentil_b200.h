@@ -113,6 +113,12 @@ int lfd_pupil_prep(const double *amp_dev, const double *opd_dev, /* n_r x n_c, r
                    int64_t out_lam_stride,      /* elements between wavelength blocks   */
                    void *stream);
 
+/* same, writing complex64 phasors (input of lfd_mft_c64x3_batched) */
+int lfd_pupil_prep_c64(const double *amp_dev, const double *opd_dev, const uint8_t *mask_dev,
+                       int32_t n_r, int32_t n_c, const lfd_segment *segs_host, int32_t nseg,
+                       const double *wavelengths_host, int32_t nlam,
+                       void *out_dev, int64_t out_lam_stride, void *stream);
+
 /* ---- K3: coherent merge + |E|^2 accumulate ---------------------------------------------
  * I[r,c] += sum over groups g of  weight_g * | sum over windows v in g covering (r,c) of E_v |^2
  * replaces lentil/field.py:231-305 (insert), :308-346 (merge), :413-461 (reduce) and
@@ -126,7 +132,7 @@ typedef struct lfd_window {
     int32_t     r0, c0;  /* position of E[0,0] in the output image (may be negative/clipped) */
     int32_t     group;   /* windows with equal group are summed coherently; groups must be
                             contiguous and non-decreasing in the array                    */
-    int32_t     pad_;
+    int32_t     c64;     /* 0: E is complex128; 1: E is complex64 (output of the K2b path)   */
     double      weight;  /* weight of the group (taken from its first window)             */
 } lfd_window;
 

@@ -42,7 +42,7 @@ class Window(C.Structure):
     _fields_ = [
         ("E", C.c_void_p), ("ld", C.c_int64),
         ("h", C.c_int32), ("w", C.c_int32), ("r0", C.c_int32), ("c0", C.c_int32),
-        ("group", C.c_int32), ("pad_", C.c_int32), ("weight", C.c_double),
+        ("group", C.c_int32), ("c64", C.c_int32), ("weight", C.c_double),
     ]
 
 
@@ -63,6 +63,9 @@ SIGNATURES = {
     "lfd_pupil_prep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                  C.POINTER(Segment), C.c_int32, C.POINTER(C.c_double), C.c_int32,
                                  C.c_void_p, C.c_int64, C.c_void_p]),
+    "lfd_pupil_prep_c64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                     C.POINTER(Segment), C.c_int32, C.POINTER(C.c_double), C.c_int32,
+                                     C.c_void_p, C.c_int64, C.c_void_p]),
     "lfd_accum_intensity": (C.c_int, [C.POINTER(Window), C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                       C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "lfd_accum_field": (C.c_int, [C.POINTER(Window), C.c_int32, C.c_void_p, C.c_int32, C.c_int32,

@@ -49,7 +49,13 @@ accum_kernel(const lfd_window *__restrict__ wins, int nwin, double *__restrict__
             }
             int rr = r - w.r0, cc = c - w.c0;
             if (rr >= 0 && rr < w.h && cc >= 0 && cc < w.w) {
-                double2 e = reinterpret_cast<const double2 *>(w.E)[(long long)rr * w.ld + cc];
+                double2 e;
+                if (w.c64) {
+                    const float2 f = reinterpret_cast<const float2 *>(w.E)[(long long)rr * w.ld + cc];
+                    e = make_double2((double)f.x, (double)f.y);
+                } else {
+                    e = reinterpret_cast<const double2 *>(w.E)[(long long)rr * w.ld + cc];
+                }
                 if (INTENSITY) {
                     sr += e.x;
                     si += e.y;

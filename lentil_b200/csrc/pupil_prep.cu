@@ -19,10 +19,16 @@ struct PupilPrepParams {
     int nseg, nlam;
 };
 
+template <typename CT> __device__ __forceinline__ CT make_cplx(double re, double im);
+template <> __device__ __forceinline__ double2 make_cplx<double2>(double re, double im) { return make_double2(re, im); }
+template <> __device__ __forceinline__ float2 make_cplx<float2>(double re, double im) { return make_float2((float)re, (float)im); }
+
+// CT = double2 (complex128, the reference's type) or float2 (complex64, input of the K2b path)
+template <typename CT>
 __global__ void __launch_bounds__(256)
 pupil_prep_kernel(const double *__restrict__ amp, const double *__restrict__ opd,
                   const uint8_t *__restrict__ mask, int n_r, int n_c,
-                  const __grid_constant__ PupilPrepParams P, double2 *__restrict__ out,
+                  const __grid_constant__ PupilPrepParams P, CT *__restrict__ out,
                   long long lam_stride) {
     const lfd_segment &sg = P.seg[blockIdx.y];
     const long long nelem = (long long)sg.h * sg.w;
@@ -33,14 +39,14 @@ pupil_prep_kernel(const double *__restrict__ amp, const double *__restrict__ opd
         double a = amp[pix];
         if (mask != nullptr && mask[(long long)sg.mask_index * n_r * n_c + pix] == 0) a = 0.0;
         double o = opd[pix];
-        double2 *dst = out + sg.out_offset + e;
+        CT *dst = out + sg.out_offset + e;
 #pragma unroll 4
         for (int l = 0; l < P.nlam; ++l) {
             double tcyc = o / P.lam[l];           // phase in cycles
             double r = tcyc - rint(tcyc);          // exact: |r| <= 0.5
             double s, c;
             sincospi(2.0 * r, &s, &c);
-            dst[(long long)l * lam_stride] = make_double2(a * c, a * s);
+            dst[(long long)l * lam_stride] = make_cplx<CT>(a * c, a * s);
         }
     }
 }
@@ -49,10 +55,10 @@ pupil_prep_kernel(const double *__restrict__ amp, const double *__restrict__ opd
 
 using namespace lfd;
 
-extern "C" int lfd_pupil_prep(const double *amp, const double *opd, const uint8_t *mask,
-                              int32_t n_r, int32_t n_c, const lfd_segment *segs, int32_t nseg,
-                              const double *wavelengths, int32_t nlam, void *out,
-                              int64_t out_lam_stride, void *stream_) {
+static int pupil_prep_impl(bool c64, const double *amp, const double *opd, const uint8_t *mask,
+                           int32_t n_r, int32_t n_c, const lfd_segment *segs, int32_t nseg,
+                           const double *wavelengths, int32_t nlam, void *out,
+                           int64_t out_lam_stride, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     LFD_REQUIRE(amp && opd && out && segs && wavelengths, "lfd_pupil_prep: NULL argument");
     LFD_REQUIRE(n_r > 0 && n_c > 0 && nseg > 0 && nlam > 0, "lfd_pupil_prep: empty problem");
@@ -78,12 +84,31 @@ extern "C" int lfd_pupil_prep(const double *amp, const double *opd, const uint8_
             long long bx = (max_elem + 255) / 256;
             if (bx > 148 * 16) bx = 148 * 16;  // grid-stride beyond 16 CTAs per SM
             dim3 grid((unsigned)bx, (unsigned)P.nseg);
-            pupil_prep_kernel<<<grid, 256, 0, stream>>>(amp, opd, mask, n_r, n_c, P,
-                                                        (double2 *)out + (long long)l0 * out_lam_stride,
-                                                        out_lam_stride);
+            if (c64)
+                pupil_prep_kernel<float2><<<grid, 256, 0, stream>>>(amp, opd, mask, n_r, n_c, P,
+                                                                    (float2 *)out + (long long)l0 * out_lam_stride,
+                                                                    out_lam_stride);
+            else
+                pupil_prep_kernel<double2><<<grid, 256, 0, stream>>>(amp, opd, mask, n_r, n_c, P,
+                                                                     (double2 *)out + (long long)l0 * out_lam_stride,
+                                                                     out_lam_stride);
             LFD_CUDA_OK(cudaGetLastError());
             count_launch();
         }
     }
     return 0;
+}
+
+extern "C" int lfd_pupil_prep(const double *amp, const double *opd, const uint8_t *mask,
+                              int32_t n_r, int32_t n_c, const lfd_segment *segs, int32_t nseg,
+                              const double *wavelengths, int32_t nlam, void *out,
+                              int64_t out_lam_stride, void *stream) {
+    return pupil_prep_impl(false, amp, opd, mask, n_r, n_c, segs, nseg, wavelengths, nlam, out, out_lam_stride, stream);
+}
+
+extern "C" int lfd_pupil_prep_c64(const double *amp, const double *opd, const uint8_t *mask,
+                                  int32_t n_r, int32_t n_c, const lfd_segment *segs, int32_t nseg,
+                                  const double *wavelengths, int32_t nlam, void *out,
+                                  int64_t out_lam_stride, void *stream) {
+    return pupil_prep_impl(true, amp, opd, mask, n_r, n_c, segs, nseg, wavelengths, nlam, out, out_lam_stride, stream);
 }

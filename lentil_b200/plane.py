@@ -271,9 +271,11 @@ class Plane(_PlaneBase):
     def _phasors_into(self, buf, wavelengths, ops, opd_dev=None):
         """K1 into rows of an existing (nlam, total) buffer, optionally with another OPD map
         (a Monte-Carlo realisation) in place of the plane's own."""
+        import torch
         lam = np.ascontiguousarray(wavelengths, dtype=np.float64).reshape(-1)
         opd = ops['opd'] if opd_dev is None else opd_dev
-        rc = _lib.lib().lfd_pupil_prep(
+        fn = _lib.lib().lfd_pupil_prep_c64 if buf.dtype == torch.complex64 else _lib.lib().lfd_pupil_prep
+        rc = fn(
             ops['amp'].data_ptr(), opd.data_ptr(),
             ops['mask'].data_ptr() if ops['mask'] is not None else None,
             ops['shape'][0], ops['shape'][1], ops['segs'], ops['nseg'],

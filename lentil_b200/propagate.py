@@ -142,7 +142,7 @@ def _shift_for(tilts, z, wavelength, du, oversample):
 
 def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, oversample=2,
                         mask=None, weights=None, tilts=None, opds=None, out=None, chunk_bytes=8 << 30,
-                        distributed=False, return_device=False):
+                        distributed=False, return_device=False, precision='c128'):
     """Polychromatic, multi-field-point, multi-realisation PSF stack in one call.
 
     Equivalent to the reference user loop (docs/user/performance.rst:44-49)::
@@ -162,13 +162,21 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
     out : optional float64 device tensor to accumulate into, shape ([R,] [P,] H, W)
     distributed : shard the wavelengths over torch.distributed ranks and all-reduce the stack
     return_device : return the device tensor instead of a numpy array
+    precision : 'c128' (default: lentil's arithmetic, FP64 tensor cores) or 'c64' (complex64 fields
+        through the 3xTF32 tcgen05 path K2b; intensities are still accumulated in float64;
+        peak-normalised PSF error ~1e-6 .. 1e-5)
 
     Returns ([R,] [P,] H, W): axes that were not requested are squeezed away.
 
     Host work is O(field points x segments) window planning plus numpy-vectorised descriptor
     tables (one row per plane); everything per-pixel runs in K1 / K2a / K3.
     """
+    import torch
     from .plane import Tilt
+    if precision not in ('c128', 'c64'):
+        raise ValueError("precision must be 'c128' or 'c64'")
+    c64 = precision == 'c64'
+    cdtype, esize = (torch.complex64, 8) if c64 else (torch.complex128, 16)
     wavelengths = np.asarray(wavelengths, dtype=float).reshape(-1)
     L = len(wavelengths)
     weights = np.ones(L) if weights is None else np.asarray(weights, dtype=float).reshape(-1)
@@ -232,7 +240,7 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
         cr, cl = wf_r[c0:c0 + step], wf_l[c0:c0 + step]
         lam = wavelengths[cl]
         nw = len(lam)
-        phasors = device.empty_c128(nw, ops['total'])
+        phasors = torch.empty(nw, ops['total'], dtype=cdtype, device=device.device())
         for r in np.unique(cr):                                            # K1, one launch per realisation
             sel = np.flatnonzero(cr == r)
             plane._phasors_into(phasors[int(sel[0]):int(sel[-1]) + 1], lam[sel], ops,
@@ -266,12 +274,12 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
             continue
         sizes = jshape[:, 0] * jshape[:, 1]
         pos = np.concatenate(([0], np.cumsum(sizes)[:-1]))
-        buf = device.empty_c128(int(sizes.sum()))
-        # ---- K2a descriptors, one row per plane -------------------------------------------------
+        buf = torch.empty(int(sizes.sum()), dtype=cdtype, device=device.device())
+        # ---- K2a / K2b descriptors, one row per plane -------------------------------------------------
         D = np.zeros(nj, dtype=np.dtype(_lib.MftDesc))
-        D['f'] = phasors.data_ptr() + 16 * (jw * ops['total'] + seg_off[jn])
+        D['f'] = phasors.data_ptr() + esize * (jw * ops['total'] + seg_off[jn])
         D['ldf'] = seg_w[jn]
-        D['out'] = buf.data_ptr() + 16 * pos
+        D['out'] = buf.data_ptr() + esize * pos
         D['ldo'] = jshape[:, 1]
         D['m'], D['n'] = seg_h[jn], seg_w[jn]
         D['M'], D['N'] = jshape[:, 0], jshape[:, 1]
@@ -282,7 +290,7 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
         D['unitary'] = 1
         for b0 in range(0, nj, _MAX_PLANES_PER_LAUNCH):                      # K2a
             nb = min(_MAX_PLANES_PER_LAUNCH, nj - b0)
-            _fourier.run_mft(D[b0:b0 + nb].ctypes.data_as(C.POINTER(_lib.MftDesc)), nb)
+            _fourier.run_mft(D[b0:b0 + nb].ctypes.data_as(C.POINTER(_lib.MftDesc)), nb, precision)
         # ---- K3: per output image (realisation, field point); groups = wavefronts --------------------
         Wn = np.zeros(nj, dtype=np.dtype(_lib.Window))
         Wn['E'], Wn['ld'] = D['out'], jshape[:, 1]
@@ -290,6 +298,7 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
         Wn['r0'] = H // 2 - jshape[:, 0] // 2 + jshift[:, 0]      # lentil/field.py:267-268
         Wn['c0'] = W // 2 - jshape[:, 1] // 2 + jshift[:, 1]
         Wn['group'] = jw
+        Wn['c64'] = 1 if c64 else 0
         Wn['weight'] = weights[cl][jw]
         img = cr[jw] * P + jp
         for im in np.unique(img):

@@ -47,3 +47,26 @@ def test_c64_psf_error_on_a_pupil():
     ref = oc.dft2(f, alpha, shape=(512, 512))
     I, Iref = np.abs(F.astype(np.complex128)) ** 2, np.abs(ref) ** 2
     assert np.max(np.abs(I - Iref)) / np.max(Iref) <= TOL32
+
+
+def test_batch_pipeline_c64_against_oracle():
+    """K1 (complex64 phasors) -> K2b -> K3 (float64 accumulation) through propagate_dft_batch."""
+    from lentil_b200 import synth
+    rng = np.random.default_rng(5)
+    mask = synth.annulus((256, 256), 120)
+    amp = synth.normalize_power(mask)
+    opd = synth.zernike_opd(mask, rng.normal(size=12) * 30e-9)
+    dx, z, du = 1 / 240, 20.0, 5e-6
+    wls = np.linspace(500e-9, 900e-9, 6)
+    wts = np.full(6, 1 / 6)
+    tilts = [[0.0, 0.0], [7e-6, -3e-6]]
+    p = lentil.Pupil(amplitude=amp, opd=opd, pixelscale=dx, focal_length=z)
+    stack = lentil.propagate_dft_batch(p, wls, du, (128, 128), oversample=2, weights=wts, tilts=tilts, precision='c64')
+    ref64 = lentil.propagate_dft_batch(p, wls, du, (128, 128), oversample=2, weights=wts, tilts=tilts)
+    assert stack.shape == (2, 256, 256) and stack.dtype == np.float64
+    for k, t in enumerate(tilts):
+        ref = oc.psf(amp, opd, None, wls, wts, (dx, dx), z, du, (128, 128), None, 2, wf_tilt=t)
+        assert peak_err(stack[k], ref) <= TOL32
+        assert peak_err(ref64[k], ref) <= 1e-10
+    with pytest.raises(ValueError):
+        lentil.propagate_dft_batch(p, wls, du, (128, 128), precision='fp16')
