@@ -259,6 +259,25 @@ def run_ours(args):
     planes = w["nlam"] * world * args.steps
     value = planes / (ms * 1e-3)
 
+    # ---- optional complex64 / 3xTF32 mode (K2b, tcgen05): same workload, reported beside the FP64 headline ---
+    def step_c64():
+        return lentil.propagate_dft_batch(pupil, wls, w["du"], shape, oversample=w["oversample"], weights=wts,
+                                          distributed=world > 1, return_device=True, precision="c64")
+    for _ in range(3):
+        psf32 = step_c64()
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(args.steps):
+        psf32 = step_c64()
+    c1.record()
+    barrier()
+    t = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    c64_value = planes / (float(t[0]) * 1e-3)
+    c64_err = float((psf32 - psf).abs().max() / psf.max())
+
     # ---- e2e: public API, host arrays in (pinned), numpy PSF out, copies inside the timed region ---
     amp_pin = torch.from_numpy(amp).pin_memory()
     opd_pin = torch.from_numpy(opd).pin_memory()
@@ -353,6 +372,8 @@ def run_ours(args):
                          "sample": f"{cpu_planes} of the {w['nlam']} wavelengths (evenly spaced) in {cpu_s:.1f} s, "
                                    "full Wavefront*Pupil -> propagate_dft -> insert per wavelength"},
         "parity_peak_normalised_error": parity,
+        "c64_3xtf32": {"value": c64_value, "unit": "planes/s", "peak_normalised_error_vs_fp64": c64_err,
+                       "note": "optional complex64 mode (K2b: tcgen05 kind::tf32, TMEM accumulators); gate 1e-5"},
     }
     print(json.dumps(line))
     if dist is not None:

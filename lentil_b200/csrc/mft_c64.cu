@@ -9,9 +9,11 @@
 // TRUNCATES — a coherent sum loses ~4e-8 of its magnitude per MMA accumulation, always downwards.
 // The small hi*lo and lo*hi corrections therefore go to their own TMEM accumulators and are added
 // to the hi*hi sum once, in the epilogue (round-to-nearest), so the large accumulator sees one
-// rounding per k-block instead of three.  Peak-normalised PSF error: ~1e-6 on incoherent data,
-// ~1e-7 x (folded K / 8) at a coherent PSF peak (6e-6 for the 1001^2 pupil of BASELINE config 2);
-// gate 1e-5 (BASELINE.json north_star).
+// rounding per k-block instead of three.  What remains is a loss of TRUNC_LOSS_PER_PRODUCT x K
+// (relative) on a fully coherent sum — the same constant for K = 121, 251 and 501 — and ~0 on an
+// incoherent one; the epilogue multiplies by (1 + TRUNC_LOSS_PER_PRODUCT x K), which cancels the
+// expected loss at a PSF peak and perturbs any other element by at most that fraction of its own
+// magnitude.  Peak-normalised PSF error after compensation: ~1e-6 .. 4e-6 (gate 1e-5).
 //
 // Per CTA (one tile = 256 folded rows x 32 complex columns, K looped in blocks of 8):
 //   warp 0        : TMEM alloc; one lane issues 12 UMMAs (128x64x8) per k-block and commits
@@ -39,6 +41,8 @@ constexpr int TN = 32;        // complex columns per CTA = 64 real columns (UMMA
 constexpr int NR = 2 * TN;    // UMMA N
 constexpr int HALF = TN / 2;  // FOLD_OUT: folded columns per tile (HALF columns j+ and their HALF mirrors)
 constexpr int KB = 8;         // folded K per k-block (UMMA K for tf32)
+// measured with scripts/gpu_c64.py (all-ones input, coherent everywhere): relative loss per accumulated product
+constexpr double TRUNC_LOSS_PER_PRODUCT = 6.2e-9;
 constexpr int NA = 3;         // twiddle (A operand) stages, 32 KB each
 constexpr int NB = 12;        // data (B operand) slots, 8 KB each: a deeper ring, because the data comes from
                               // L2/HBM (~2000 cycles) while a k-block of MMAs lasts ~400
@@ -611,6 +615,7 @@ int launch_mft_c64(const lfd_mft_desc *descs, int count, void *workspace, size_t
         s1.nKf = g.Kf2; s1.nKpad = g.Kpad2; s1.nhm = p.n / 2; s1.ncR2 = cRn; s1.nKfp = g.nKfp;
         s1.alpha = p.alpha_r; s1.oprime = p.off_r - 0.5 * cRm; s1.sprime = p.shift_r + 0.5 * cUM; s1.scale = 1.0;
         s1.nalpha = p.alpha_c; s1.nsprime = p.shift_c + 0.5 * cUN;
+        s1.scale *= 1.0 + TRUNC_LOSS_PER_PRODUCT * g.Kf1;
 
         CStage &s2 = hs[count + i];
         s2.B = B2; s2.plane = s1.nplane; s2.Kf = g.Kf2; s2.Kpad = g.Kpad2; s2.C = p.M; s2.Npad = g.Npad2;
@@ -621,6 +626,7 @@ int launch_mft_c64(const lfd_mft_desc *descs, int count, void *workspace, size_t
         s2.nKf = 0; s2.nKpad = 0; s2.nhm = 0; s2.ncR2 = 0; s2.nKfp = 0;
         s2.alpha = p.alpha_c; s2.oprime = p.off_c - 0.5 * cRn; s2.sprime = p.shift_c + 0.5 * cUN; s2.scale = scale;
         s2.nalpha = 0.0; s2.nsprime = 0.0;
+        s2.scale *= 1.0 + TRUNC_LOSS_PER_PRODUCT * g.Kf2;
 
         const int t1 = 12 * g.Rfp1 + g.nKfp, t2 = 12 * g.Rfp2;
         if (t1 > max_tab) max_tab = t1;
