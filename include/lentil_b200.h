@@ -154,6 +154,23 @@ int lfd_field_mul(const void *a_dev, int64_t lda, const void *b_dev, int64_t ldb
                   double s_re, double s_im, void *out_dev, int64_t ldo,
                   int32_t h, int32_t w, void *stream);
 
+/* ---- fit_tilt -------------------------------------------------
+ * Per-segment least-squares fit of [1, r*dx0, -c*dx1] to the OPD over the segment mask and removal
+ * of the two tilt terms: replaces Plane.fit_tilt / ptt_vector, lentil/plane.py:522-611.
+ * lfd_fit_tilt_moments reduces, per segment, the 9 moments S1 Sx Sy Sxx Sxy Syy Sz Sxz Syz with x, y
+ * measured from the centre of the segment's bounding box (x_c = (r0 + (h-1)/2 - n_r/2)*dx0,
+ * y_c = -(c0 + (w-1)/2 - n_c/2)*dx1); the caller solves the 3x3 systems.  mask_dev: uint8 cube
+ * (nmask x n_r x n_c) or NULL, in which case the mask is amp_for_mask != 0 (lentil/plane.py:43-47). */
+int lfd_fit_tilt_moments(const double *opd_dev, const uint8_t *mask_dev, const double *amp_for_mask_dev,
+                         int32_t n_r, int32_t n_c, double dx0, double dx1,
+                         const lfd_segment *segs_host, int32_t nseg, double *moments_dev /* nseg x 9 */,
+                         void *scratch_dev, size_t scratch_bytes /* >= nseg * 40 */, void *stream);
+/* out = opd with each segment's tilt removed: (opd - t1*x*m - t2*y*m) summed over segments
+ * (single segment: pixels outside the mask keep their OPD).  coef_dev: nseg x 3 (piston, t1, t2). */
+int lfd_remove_tilt(const double *opd_dev, const uint8_t *mask_dev, const double *amp_for_mask_dev,
+                    int32_t n_r, int32_t n_c, int32_t nseg, double dx0, double dx1,
+                    const double *coef_dev, double *out_dev, void *stream);
+
 /* ---- host-buffer convenience layer (what bench.py's e2e leg and the numpy shim call) ------
  * A context owns a device workspace, pinned staging buffers and one stream on `device`.
  */

@@ -344,39 +344,52 @@ class Plane(_PlaneBase):
 
     def fit_tilt(self, inplace=False):
         """Least-squares fit and removal of per-segment tilt from the OPD; the equivalent angles
-        are kept as Tilt objects in ``self.tilt`` (lentil/plane.py:564-611).  Solved on the
-        masked pixels only — rows outside the mask are zero in the reference's design matrix and
-        cannot influence its minimum-norm solution."""
+        are kept as Tilt objects in ``self.tilt`` (lentil/plane.py:564-611).
+
+        Runs on the device (lfd_fit_tilt_moments + lfd_remove_tilt): the reference's dense
+        (npix x 3) design matrix per segment has zero rows outside the mask, so its lstsq solution
+        is that of the 3x3 normal equations over the masked pixels; the nine moments per segment
+        are reduced on the GPU, the 3x3 systems solved here."""
         plane = self if inplace else copy.deepcopy(self)
         if plane.shape == () or plane.shape is None or plane.opd.size == 1:
             return plane
         if plane.pixelscale is None:
             raise ValueError("can't create ptt_vector with pixelscale = ()")
         ps = np.broadcast_to(plane.pixelscale, (2,))
-        r, c = helper.mesh(plane.shape)
-        basis = (np.ones(r.shape), r * ps[0], -c * ps[1])
-        opd = np.array(plane.opd, dtype=float)
-        masks = plane.mask.reshape((plane.size,) + tuple(plane.shape))
-
-        def solve(mk):
-            sel = mk != 0
-            w = mk[sel].astype(float)
-            A = np.stack([b[sel] * w for b in basis], axis=1)
-            return np.linalg.lstsq(A, opd[sel], rcond=None)[0]
-
-        if plane.size == 1:
-            t = solve(masks[0])
-            plane.opd = opd - (basis[1] * masks[0] * t[1] + basis[2] * masks[0] * t[2])
-            plane.tilt.append(Tilt(x=t[1], y=t[2]))
-        else:
-            new = np.zeros_like(opd)
-            ts = []
-            for mk in masks:
-                t = solve(mk)
-                ts.append(t)
-                new += (opd - (basis[1] * mk * t[1] + basis[2] * mk * t[2])) * mk
-            plane.opd = new
-            plane.tilt.extend(Tilt(x=t[1], y=t[2]) for t in ts)
+        ops = plane._operands()
+        if ops['scalar'] is not None:
+            return plane
+        if ops['mask'] is None and not (plane._mask is None and type(plane).__mask__ is _PlaneBase.__mask__):
+            raise NotImplementedError('fit_tilt with a non-binary mask is not supported')
+        nseg, (n_r, n_c) = ops['nseg'], ops['shape']
+        L = _lib.lib()
+        mask_ptr = ops['mask'].data_ptr() if ops['mask'] is not None else None
+        moments = device.zeros_f64(nseg * 9)
+        scratch = device.empty_bytes(64 * nseg)
+        _lib.check(L.lfd_fit_tilt_moments(ops['opd'].data_ptr(), mask_ptr, ops['amp'].data_ptr(), n_r, n_c,
+                                          float(ps[0]), float(ps[1]), ops['segs'], nseg, moments.data_ptr(),
+                                          scratch.data_ptr(), scratch.numel(), device.stream_ptr()),
+                   "lfd_fit_tilt_moments")
+        m = device.to_host(moments).reshape(nseg, 9)
+        coef = np.zeros((nseg, 3))
+        for k in range(nseg):
+            s1, sx, sy, sxx, sxy, syy, sz, sxz, syz = m[k]
+            nmat = np.array([[s1, sx, sy], [sx, sxx, sxy], [sy, sxy, syy]])
+            sol = np.linalg.solve(nmat, np.array([sz, sxz, syz]))
+            sg = ops['segs'][k]
+            xc = (sg.r0 + 0.5 * (sg.h - 1) - n_r // 2) * ps[0]
+            yc = -(sg.c0 + 0.5 * (sg.w - 1) - n_c // 2) * ps[1]
+            coef[k] = (sol[0] - sol[1] * xc - sol[2] * yc, sol[1], sol[2])
+        coef_dev = device.to_dev(coef, dtype=np.float64)
+        out = device.zeros_f64(n_r, n_c)
+        _lib.check(L.lfd_remove_tilt(ops['opd'].data_ptr(), mask_ptr, ops['amp'].data_ptr(), n_r, n_c, nseg,
+                                     float(ps[0]), float(ps[1]), coef_dev.data_ptr(), out.data_ptr(),
+                                     device.stream_ptr()), "lfd_remove_tilt")
+        frozen = plane._frozen
+        plane._frozen = False
+        plane.opd = device.to_host(out)
+        plane._frozen = frozen
+        plane.tilt.extend(Tilt(x=c[1], y=c[2]) for c in coef)
         plane._dev_cache = None
         return plane
 

@@ -316,3 +316,37 @@ def test_monte_carlo_opd_stack_against_oracle():
     assert peak_err(s2[:, 0], stack[:2]) <= 1e-13
     ref = oc.psf(amp, opds[1], None, wls, wts, (dx, dx), z, du, (48, 48), None, 2, wf_tilt=tilts[1])
     assert peak_err(s2[1, 1], ref) <= TOL64
+
+
+def test_fit_tilt_recovers_a_plane():
+    rng = np.random.default_rng(8)
+    n, dx = 48, 1 / 40
+    amp = synth.circle((n, n), 18)
+    rr, cc = lentil.helper.mesh((n, n))
+    opd = (2e-7 + 3e-6 * rr * dx - 1.5e-6 * (-cc) * dx) * amp
+    p = lentil.Pupil(amplitude=amp, opd=opd, pixelscale=dx, focal_length=5.0)
+    q = p.fit_tilt(inplace=False)
+    assert q is not p and len(p.tilt) == 0 and len(q.tilt) == 1
+    assert np.allclose(q.opd[amp > 0], 2e-7, atol=1e-15)
+    assert np.isclose(q.tilt[0].y, 3e-6) and np.isclose(q.tilt[0].x, -1.5e-6)
+    assert p.fit_tilt(inplace=True) is p
+    assert lentil.Image(amplitude=amp).fit_tilt() is not None
+
+
+def test_fit_tilt_equals_tilt_in_opd():
+    # reference tests/test_propagate.py:45-70: PSF centroid with fit_tilt == with the tilt left in the OPD
+    rng = np.random.default_rng(12)
+    mask = synth.circle((256, 256), 120)
+    amp = synth.normalize_power(mask)
+    coeffs = np.concatenate(([0.0], 5e-6 * rng.uniform(-0.5, 0.5, 2)))
+    opd = synth.zernike_opd(mask, coeffs)
+    p = lentil.Pupil(amplitude=amp, opd=opd, pixelscale=1 / 240, focal_length=10.0)
+    a = lentil.propagate_dft(lentil.Wavefront(650e-9) * p, shape=128, pixelscale=5e-6, oversample=2).intensity
+    q = p.fit_tilt()
+    b = lentil.propagate_dft(lentil.Wavefront(650e-9) * q, shape=128, pixelscale=5e-6, oversample=2).intensity
+    a[a < 1e-5] = 0
+    b[b < 1e-5] = 0
+    rr, cc = np.indices(a.shape)
+    ca = np.array([np.sum(rr * a), np.sum(cc * a)]) / np.sum(a)
+    cb = np.array([np.sum(rr * b), np.sum(cc * b)]) / np.sum(b)
+    assert np.all(np.abs(ca - cb) <= 1e-6)

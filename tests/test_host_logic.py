@@ -213,19 +213,3 @@ def test_freeze_semantics():
     p.thaw()
     p.opd = np.ones((4, 4))
     assert p.size == 1 and p.shape == (4, 4)
-
-
-def test_fit_tilt_recovers_a_plane():
-    rng = np.random.default_rng(8)
-    n, dx = 48, 1 / 40
-    from lentil_b200 import synth
-    amp = synth.circle((n, n), 18)
-    rr, cc = helper.mesh((n, n))
-    opd = (2e-7 + 3e-6 * rr * dx - 1.5e-6 * (-cc) * dx) * amp
-    p = lentil.Pupil(amplitude=amp, opd=opd, pixelscale=dx, focal_length=5.0)
-    q = p.fit_tilt(inplace=False)
-    assert q is not p and len(p.tilt) == 0 and len(q.tilt) == 1
-    assert np.allclose(q.opd[amp > 0], 2e-7, atol=1e-15)
-    assert np.isclose(q.tilt[0].y, 3e-6) and np.isclose(q.tilt[0].x, -1.5e-6)
-    assert p.fit_tilt(inplace=True) is p
-    assert lentil.Image(amplitude=amp).fit_tilt() is not None
