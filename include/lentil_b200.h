@@ -171,6 +171,13 @@ int lfd_remove_tilt(const double *opd_dev, const uint8_t *mask_dev, const double
                     int32_t n_r, int32_t n_c, int32_t nseg, double dx0, double dx1,
                     const double *coef_dev, double *out_dev, void *stream);
 
+/* Bounding box (rmin, rmax, cmin, cmax; inclusive) of the support of each of `nplanes` mask planes
+ * (n_r x n_c, uint8 or float64): entries > 0, or != 0 when `nonzero` (a mask derived from an
+ * amplitude, lentil/plane.py:43-47).  An empty plane yields (n_r, -1, n_c, -1).
+ * replaces lentil/util.py:190-218 (boundary) under helper.boundary_slice / plane._plane_slice. */
+int lfd_mask_bbox(const void *x_dev, int32_t is_f64, int32_t nonzero, int32_t n_r, int32_t n_c,
+                  int32_t nplanes, int32_t *out_dev /* 4 x nplanes */, void *stream);
+
 /* ---- host-buffer convenience layer (what bench.py's e2e leg and the numpy shim call) ------
  * A context owns a device workspace, pinned staging buffers and one stream on `device`.
  */

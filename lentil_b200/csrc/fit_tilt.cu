@@ -80,9 +80,59 @@ remove_tilt_kernel(const double *__restrict__ opd, const uint8_t *__restrict__ m
     }
 }
 
+// ---- bounding box of the support of each mask plane (lentil/util.py:190-218 boundary) -----------------
+// out[4p .. 4p+3] = rmin, rmax, cmin, cmax of plane p (initialised to n_r, -1, n_c, -1 by the launcher)
+template <typename T>
+__global__ void __launch_bounds__(256)
+bbox_kernel(const T *__restrict__ x, int n_r, int n_c, int nonzero, int *__restrict__ out) {
+    const long long npix = (long long)n_r * n_c;
+    const T *plane = x + (long long)blockIdx.y * npix;
+    int rmin = n_r, rmax = -1, cmin = n_c, cmax = -1;
+    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
+         pix += (long long)gridDim.x * blockDim.x) {
+        const T v = plane[pix];
+        const bool hit = nonzero ? (v != (T)0) : (v > (T)0);
+        if (hit) {
+            const int r = (int)(pix / n_c), c = (int)(pix % n_c);
+            rmin = min(rmin, r); rmax = max(rmax, r); cmin = min(cmin, c); cmax = max(cmax, c);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
+        rmax = max(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+        cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+        cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+    }
+    if ((threadIdx.x & 31) == 0 && rmax >= 0) {
+        int *o4 = out + 4 * blockIdx.y;
+        atomicMin(o4 + 0, rmin); atomicMax(o4 + 1, rmax); atomicMin(o4 + 2, cmin); atomicMax(o4 + 3, cmax);
+    }
+}
+
+__global__ void bbox_init_kernel(int *out, int nplanes, int n_r, int n_c) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < nplanes) { out[4 * p] = n_r; out[4 * p + 1] = -1; out[4 * p + 2] = n_c; out[4 * p + 3] = -1; }
+}
+
 }  // namespace lfd
 
 using namespace lfd;
+
+extern "C" int lfd_mask_bbox(const void *x, int32_t is_f64, int32_t nonzero, int32_t n_r, int32_t n_c,
+                             int32_t nplanes, int32_t *out_dev, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    LFD_REQUIRE(x && out_dev && n_r > 0 && n_c > 0 && nplanes > 0, "lfd_mask_bbox: bad arguments");
+    bbox_init_kernel<<<(nplanes + 127) / 128, 128, 0, stream>>>(out_dev, nplanes, n_r, n_c);
+    long long npix = (long long)n_r * n_c, bx = (npix + 255) / 256;
+    if (bx > 148 * 8) bx = 148 * 8;
+    dim3 grid((unsigned)bx, (unsigned)nplanes);
+    if (is_f64) bbox_kernel<double><<<grid, 256, 0, stream>>>((const double *)x, n_r, n_c, nonzero, out_dev);
+    else bbox_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t *)x, n_r, n_c, nonzero, out_dev);
+    LFD_CUDA_OK(cudaGetLastError());
+    count_launch(2);
+    return 0;
+}
 
 extern "C" int lfd_fit_tilt_moments(const double *opd, const uint8_t *mask, const double *amp_for_mask,
                                     int32_t n_r, int32_t n_c, double dx0, double dx1,

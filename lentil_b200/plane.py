@@ -207,48 +207,82 @@ class Plane(_PlaneBase):
     # ---- device-side operands -------------------------------------------------------------------
     def _operands(self):
         """Host metadata + device copies of (amplitude, opd, mask) for K1.  Uploaded once per
-        multiply, or once per freeze() when the plane is frozen."""
+        multiply, or once per freeze() when the plane is frozen.  The per-segment bounding boxes
+        (helper.boundary_slice in the reference, recomputed there on every multiply) come from a
+        device reduction over the uploaded mask (lfd_mask_bbox)."""
         if self.frozen and self._dev_cache is not None:
             return self._dev_cache
+        import torch
         amp, opd = np.asarray(self.amplitude), np.asarray(self.opd)
         # When the mask is the default one derived from the amplitude (plane.py:43-47:
         # amplitude.astype(bool)) then amp*mask == amp, so K1 needs no mask plane and only the
         # bounding box has to be found (same pixels: amp != 0).
         derived = self._mask is None and type(self).__mask__ is _PlaneBase.__mask__
-        mask = (amp != 0) if derived else np.asarray(self.mask)
-        nseg = 1 if mask.ndim < 3 else mask.shape[0]
-        shape = tuple(mask.shape) if nseg == 1 else tuple(mask.shape[1:])
-        slices = _plane_slice(mask)
-        ops = {'nseg': nseg, 'shape': shape, 'slices': slices, 'scalar': None}
         if amp.size == 1 and opd.size == 1:
-            ops['scalar'] = (amp, opd)
+            mask = (amp != 0) if derived else np.asarray(self.mask)
+            nseg = 1 if mask.ndim < 3 else mask.shape[0]
+            shape = tuple(mask.shape) if nseg == 1 else tuple(mask.shape[1:])
+            ops = {'nseg': nseg, 'shape': shape, 'pshape': shape, 'slices': _plane_slice(mask), 'scalar': (amp, opd)}
+            if self.frozen:
+                self._dev_cache = ops
+            return ops
+
+        mask = None if derived else np.asarray(self.mask)
+        full = False
+        if derived:
+            shape, nseg = tuple(amp.shape), 1
+            if len(shape) != 2:
+                # scalar amplitude with an array opd (a phase-only plane): the derived mask is a scalar, the
+                # plane has no shape of its own and the phasor covers the whole opd array (plane.py:496-507)
+                shape, full = tuple(opd.shape), True
+                if len(shape) != 2:
+                    raise ValueError('opd must be a scalar or a 2-D array')
         else:
+            nseg = 1 if mask.ndim < 3 else mask.shape[0]
+            shape = tuple(mask.shape) if nseg == 1 else tuple(mask.shape[1:])
             if len(shape) != 2:
                 raise ValueError('array amplitude/opd need a 2-D (or 3-D segment) mask')
-            use_mask = amp.size != 1 and not derived   # plane.py:503 — a scalar amplitude is not masked
-            if use_mask:
-                mk = mask.reshape((nseg,) + shape)
-                binary = mk.dtype == bool or np.all((mk == 0) | (mk == 1))
-                if not binary:
+        ops = {'nseg': nseg, 'shape': shape, 'pshape': () if full else shape, 'scalar': None}
+        use_mask = amp.size != 1 and not derived   # plane.py:503 — a scalar amplitude is not masked
+        mk_dev = None
+        if mask is not None:
+            mk = mask.reshape((nseg,) + shape)
+            if mk.dtype == bool:
+                mk8 = mk.view(np.uint8)
+            else:
+                binary = np.all((mk == 0) | (mk == 1))
+                if not binary and use_mask:
                     if nseg > 1:
                         raise NotImplementedError('non-binary segment masks are not supported')
                     amp, use_mask = amp * mk[0], False
-            ops['amp'] = device.to_dev(amp if amp.shape == shape else np.broadcast_to(amp, shape), dtype=np.float64)
-            ops['opd'] = device.to_dev(opd if opd.shape == shape else np.broadcast_to(opd, shape), dtype=np.float64)
-            ops['mask'] = device.to_dev(mk.astype(np.uint8)) if use_mask else None
-            segs = (_lib.Segment * nseg)()
-            total = 0
-            for k, s in enumerate(slices):
-                if s is Ellipsis:
-                    r0, r1, c0, c1 = 0, shape[0], 0, shape[1]
-                else:
-                    r0, r1, c0, c1 = int(s[0].start), int(s[0].stop), int(s[1].start), int(s[1].stop)
-                segs[k].r0, segs[k].c0, segs[k].h, segs[k].w = r0, c0, r1 - r0, c1 - c0
-                segs[k].mask_index = k if nseg > 1 else 0
-                segs[k].out_offset = total
-                total += (r1 - r0) * (c1 - c0)
-            ops['segs'], ops['total'] = segs, total
-            ops['offsets'] = [helper.slice_offset(s, shape) for s in slices]
+                mk8 = (mk > 0).astype(np.uint8)
+            mk_dev = device.to_dev(mk8)
+        ops['amp'] = device.to_dev(amp if amp.shape == shape else np.broadcast_to(amp, shape), dtype=np.float64)
+        ops['opd'] = device.to_dev(opd if opd.shape == shape else np.broadcast_to(opd, shape), dtype=np.float64)
+        ops['mask'] = mk_dev if use_mask else None
+        # bounding boxes on the device
+        if full:
+            bb = np.array([[0, shape[0] - 1, 0, shape[1] - 1]])
+        else:
+            bb = torch.empty(4 * nseg, dtype=torch.int32, device=device.device())
+            src, is_f64, nonzero = (ops['amp'], 1, 1) if mk_dev is None else (mk_dev, 0, 0)
+            _lib.check(_lib.lib().lfd_mask_bbox(src.data_ptr(), is_f64, nonzero, shape[0], shape[1], nseg,
+                                                bb.data_ptr(), device.stream_ptr()), "lfd_mask_bbox")
+            bb = bb.cpu().numpy().reshape(nseg, 4)
+        if np.any(bb[:, 1] < 0):
+            raise IndexError('mask plane without any data: cannot find its boundary')   # as np.where(...)[0][[0,-1]]
+        slices = [np.s_[int(b[0]):int(b[1]) + 1, int(b[2]):int(b[3]) + 1] for b in bb]
+        ops['slices'] = slices
+        segs = (_lib.Segment * nseg)()
+        total = 0
+        for k, b in enumerate(bb):
+            r0, r1, c0, c1 = int(b[0]), int(b[1]) + 1, int(b[2]), int(b[3]) + 1
+            segs[k].r0, segs[k].c0, segs[k].h, segs[k].w = r0, c0, r1 - r0, c1 - c0
+            segs[k].mask_index = k if nseg > 1 else 0
+            segs[k].out_offset = total
+            total += (r1 - r0) * (c1 - c0)
+        ops['segs'], ops['total'] = segs, total
+        ops['offsets'] = [helper.slice_offset(s, shape) for s in slices]
         if self.frozen:
             self._dev_cache = ops
         return ops
@@ -299,7 +333,7 @@ class Plane(_PlaneBase):
             raise TypeError(f"can't multiply Wavefront with ptype '{wf_pt}' by Plane with ptype '{my_pt}'")
         ops = self._operands()
         pixelscale = _mul_pixelscale(self.pixelscale, wavefront.pixelscale)
-        shape = wavefront.shape if ops['shape'] == () else ops['shape']
+        shape = wavefront.shape if ops['pshape'] == () else ops['pshape']
         out = Wavefront.empty(wavelength=wavefront.wavelength, pixelscale=pixelscale,
                               focal_length=wavefront.focal_length, shape=shape,
                               ptype=_MUL_PTYPE[wf_pt][my_pt])

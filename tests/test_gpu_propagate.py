@@ -350,3 +350,24 @@ def test_fit_tilt_equals_tilt_in_opd():
     ca = np.array([np.sum(rr * a), np.sum(cc * a)]) / np.sum(a)
     cb = np.array([np.sum(rr * b), np.sum(cc * b)]) / np.sum(b)
     assert np.all(np.abs(ca - cb) <= 1e-6)
+
+
+def test_phase_only_plane_and_explicit_nonbool_mask():
+    # scalar amplitude + array opd: the phasor covers the whole array and the plane has no shape of its own
+    rng = np.random.default_rng(21)
+    opd = rng.normal(size=(40, 50)) * 1e-7
+    w = lentil.Wavefront(600e-9) * lentil.Plane(amplitude=2.0, opd=opd)
+    assert len(w.data) == 1 and tuple(w.data[0].shape) == (40, 50) and tuple(w.data[0].offset) == (0, 0)
+    assert peak_err(w.data[0].data, 2.0 * np.exp(2j * np.pi * opd / 600e-9)) <= 1e-14
+    # explicit integer (0/1) mask smaller than the amplitude support: amp*mask and the mask's bbox are used
+    amp = np.ones((64, 64))
+    mask = np.zeros((64, 64), dtype=int)
+    mask[10:30, 20:55] = 1
+    p = lentil.Pupil(amplitude=amp, opd=np.zeros((64, 64)), mask=mask, pixelscale=1 / 60, focal_length=5.0)
+    w = lentil.Wavefront(600e-9) * p
+    f = oc.plane_multiply([oc.make_field(np.array(1, dtype=complex))], amp, np.zeros((64, 64)), mask, 600e-9)
+    assert tuple(w.data[0].shape) == f[0]["data"].shape == (20, 35)
+    assert tuple(int(v) for v in w.data[0].offset) == tuple(f[0]["offset"])
+    assert peak_err(w.data[0].data, f[0]["data"]) <= 1e-15
+    with pytest.raises(IndexError):
+        lentil.Wavefront(600e-9) * lentil.Pupil(amplitude=np.zeros((8, 8)), opd=np.zeros((8, 8)), pixelscale=1, focal_length=1)
