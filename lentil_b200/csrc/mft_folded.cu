@@ -44,6 +44,7 @@ constexpr int FTHREADS = 128;  // 4 warps stacked along the rows, each 16 folded
                                // (a twiddle element feeds 8 DMMAs); two CTAs per SM so that one CTA's
                                // prologue / epilogue hides under the other's MMAs
 constexpr int FRESEED_TILES = 64;  // re-seed the twiddle recurrence every 1024 folded K (2048 input rows)
+constexpr int FOLD_MAX_TILES = 1024;  // folded-column tiles per plane the support map can hold (inputs up to 32768 columns)
 constexpr int FIRST_WAVE_SMS = 148;  // B200: CTAs with linear id < 2*148 form the first wave
 constexpr size_t FSMEM_BYTES = (size_t)FSTAGES * 2 * FBK * FLDS * sizeof(double2);
 
@@ -53,6 +54,11 @@ struct FoldDesc {
     double2 *G;         // ge plane (Kf x C, ld = C) followed by go plane
     int K, C, Kf, hm, cR2, pad_;
     double alpha, sprime, sgn;
+    // support map for the row stage: kmax[t] = 1 + last folded row with data in folded-column tile t,
+    // kmax[ntile + t] = Kf - first such row (both start at 0 = empty; columns c and their mirrors share a
+    // tile: r2 = c - nhm  or  nhm - c - ncR2)
+    int *kmax;
+    int nhm, ncR2, ntile, pad2_;
 };
 
 struct FStageDesc {
@@ -69,6 +75,8 @@ struct FStageDesc {
     // pipe time on sincospi:  rot[Rfp] | seed[4][Rfp] | post+[Rfp] | post-[Rfp] | pre2[nKfp]
     const double2 *tab;
     int Rfp, nKfp;
+    const int *kmax;    // row stage only: K rows that actually hold data, per column tile (NULL: all)
+    int ntile, pad3_;
     // de-phasing of the two CTAs that share an SM (see mft_folded_kernel): per-launch slot counters
     // (one per SM, zeroed with the descriptor upload) and the skew in cycles (~ half a tile)
     unsigned *sm_slots;
@@ -143,19 +151,32 @@ fold_kernel(const FoldDesc *__restrict__ descs) {
     double2 *__restrict__ ge = d.G + (long long)r * d.C;
     double2 *__restrict__ go = d.G + ((long long)d.Kf + r) * d.C;
     const bool has_p = ip < d.K;
+    __shared__ int tile_nz[FOLD_MAX_TILES];
+    for (int t = threadIdx.x; t < d.ntile; t += blockDim.x) tile_nz[t] = 0;
+    __syncthreads();
     for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
         double2 a = has_p ? rowp[c] : make_double2(0.0, 0.0);
+        double2 b = center ? make_double2(0.0, 0.0) : rowm[c];
         double2 gp = make_double2(a.x * pc - a.y * ps, a.x * ps + a.y * pc);
         if (center) {
             ge[c] = gp;
             go[c] = make_double2(0.0, 0.0);
         } else {
-            double2 b = rowm[c];
             double2 gm = make_double2(b.x * pc + b.y * ps, b.y * pc - b.x * ps);   // conj(pre) * b
             ge[c] = make_double2(gp.x + gm.x, gp.y + gm.y);
             go[c] = make_double2(gp.x - gm.x, gp.y - gm.y);
         }
+        if (a.x != 0.0 || a.y != 0.0 || b.x != 0.0 || b.y != 0.0) {
+            const int r2 = (c >= d.nhm) ? (c - d.nhm) : (d.nhm - c - d.ncR2);
+            tile_nz[r2 / (FBC / 2)] = 1;                       // benign race: everybody writes 1
+        }
     }
+    __syncthreads();
+    for (int t = threadIdx.x; t < d.ntile; t += blockDim.x)
+        if (tile_nz[t]) {
+            atomicMax(d.kmax + t, r + 1);                        // 1 + last row with data
+            atomicMax(d.kmax + d.ntile + t, d.Kf - r);          // Kf - first row with data
+        }
 }
 
 // ---- folded MFT stage ---------------------------------------------------------------------------
@@ -220,11 +241,21 @@ mft_folded_kernel(const FStageDesc *__restrict__ descs) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int KT = (d.Kf + FBK - 1) / FBK;
+    // the row stage stops at the last K tile that holds data for this column tile (a disc in its bounding
+    // box leaves ~21% of them empty)
+    // ... and starts at the first one that does (a central obscuration empties the first K tiles of the
+    // central column tiles; folded K runs from the centre outwards)
+    int Kneed = d.Kf, Kfirst = 0;
+    if (FOLD_OUT && d.kmax != nullptr) {
+        Kneed = min(d.Kf, d.kmax[tc]);
+        Kfirst = max(0, d.Kf - d.kmax[d.ntile + tc]);
+    }
+    const int KT = (Kneed + FBK - 1) / FBK;
+    const int KT0 = min(Kfirst / FBK, KT);
 
 #pragma unroll
     for (int s = 0; s < FSTAGES - 1; ++s) {
-        if (s < KT) f_load_tile<FOLD_OUT>(sD + s * STAGE_ELEMS, d, s * FBK, c_base, tid);
+        if (KT0 + s < KT) f_load_tile<FOLD_OUT>(sD + s * STAGE_ELEMS, d, (KT0 + s) * FBK, c_base, tid);
         cp_async_commit();
     }
 
@@ -253,13 +284,13 @@ mft_folded_kernel(const FStageDesc *__restrict__ descs) {
         rs_[mb] = v.y;
     }
 
-    for (int kt = 0; kt < KT; ++kt) {
+    for (int kt = KT0; kt < KT; ++kt) {
         cp_async_wait<FSTAGES - 2>();
         __syncthreads();
-        if (kt == 0) { LFD_TT(1) }
+        if (kt == KT0) { LFD_TT(1) }
         {
             int nk = kt + FSTAGES - 1;
-            if (nk < KT) f_load_tile<FOLD_OUT>(sD + (nk % FSTAGES) * STAGE_ELEMS, d, nk * FBK, c_base, tid);
+            if (nk < KT) f_load_tile<FOLD_OUT>(sD + ((nk - KT0) % FSTAGES) * STAGE_ELEMS, d, nk * FBK, c_base, tid);
             cp_async_commit();
         }
         if (kt == 0) {
@@ -269,14 +300,14 @@ mft_folded_kernel(const FStageDesc *__restrict__ descs) {
                 tc_[mb] = v.x;
                 ts_[mb] = v.y;
             }
-        } else if ((kt % FRESEED_TILES) == 0) {                          // very long K only
+        } else if (kt == KT0 || (kt % FRESEED_TILES) == 0) {             // late start or very long K
             const double rp = (double)(kt * FBK + t) + cR;               // R' of this lane's K slot
             double sc, ss;
             cis_cycles(d.alpha, rp, up0, 1.0, tc_[0], ts_[0]);
             cis_cycles(d.alpha, rp, 8.0, 1.0, sc, ss);
             cmul(tc_[0], ts_[0], sc, ss, tc_[1], ts_[1]);
         }
-        const double2 *se = sD + (kt % FSTAGES) * STAGE_ELEMS + g;
+        const double2 *se = sD + ((kt - KT0) % FSTAGES) * STAGE_ELEMS + g;
         const double2 *so = se + FBK * FLDS;
 
 #pragma unroll
@@ -413,7 +444,9 @@ constexpr long long SKEW_CYCLES_PER_KTILE = 2400;   // half of the ~4.7k cycles 
 constexpr size_t SLOT_BYTES = 2 * 256 * sizeof(unsigned);   // per-SM slot counters, one set per MFT launch
 
 size_t folded_workspace_bytes(const lfd_mft_desc *descs, int count) {
-    size_t bytes = f_align((size_t)count * (sizeof(FoldDesc) + 2 * sizeof(FStageDesc)) + SLOT_BYTES, 256);
+    size_t kmax_ints = 0;
+    for (int i = 0; i < count; ++i) kmax_ints += 2 * (((descs[i].n + 1) / 2 + FBC / 2 - 1) / (FBC / 2));
+    size_t bytes = f_align((size_t)count * (sizeof(FoldDesc) + 2 * sizeof(FStageDesc)) + SLOT_BYTES + kmax_ints * sizeof(int), 256);
     for (int i = 0; i < count; ++i) {
         const lfd_mft_desc &p = descs[i];
         bytes += f_align((size_t)2 * ((p.m + 1) / 2) * p.n * sizeof(double2), 256);
@@ -440,12 +473,15 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
         attr_set = true;
     }
     const size_t desc_bytes = (size_t)count * (sizeof(FoldDesc) + 2 * sizeof(FStageDesc));
-    const size_t hdr_bytes = desc_bytes + SLOT_BYTES;
+    size_t kmax_ints = 0;
+    for (int i = 0; i < count; ++i) kmax_ints += 2 * (((descs[i].n + 1) / 2 + FBC / 2 - 1) / (FBC / 2));
+    const size_t hdr_bytes = desc_bytes + SLOT_BYTES + kmax_ints * sizeof(int);   // counters and support maps start at zero
     char *h = (char *)calloc(hdr_bytes, 1);                 // slot counters start at zero
     LFD_REQUIRE(h != nullptr, "out of host memory");
     FoldDesc *hf = (FoldDesc *)h;
     FStageDesc *hs = (FStageDesc *)(h + (size_t)count * sizeof(FoldDesc));
     unsigned *slots_dev = (unsigned *)((char *)workspace + desc_bytes);
+    int *kmax_dev = (int *)((char *)workspace + desc_bytes + SLOT_BYTES);
     char *ws = (char *)workspace;
     size_t off = f_align(hdr_bytes, 256);
     int max_rows = 0, max_t1 = 0, max_t2 = 0, max_tab = 0;
@@ -476,6 +512,9 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
         fd.D = (const double2 *)p.f; fd.ldd = p.ldf; fd.G = G1;
         fd.K = p.m; fd.C = p.n; fd.Kf = Kf1; fd.hm = p.m / 2; fd.cR2 = cRm; fd.pad_ = 0;
         fd.alpha = p.alpha_r; fd.sprime = p.shift_r + 0.5 * cUM; fd.sgn = sgn;
+        fd.nhm = p.n / 2; fd.ncR2 = cRn; fd.ntile = (Kf2 + FBC / 2 - 1) / (FBC / 2); fd.pad2_ = 0;
+        fd.kmax = kmax_dev;
+        if (fd.ntile > FOLD_MAX_TILES) { free(h); LFD_REQUIRE(false, "lfd_mft_c128_batched: plane %d is too wide (%d columns)", i, p.n); }
         if (Kf1 > max_rows) max_rows = Kf1;
 
         // stage 1 (rows): K = m, C = n, output rows M; result folded along its columns for stage 2
@@ -488,6 +527,7 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
         s1.nKf = Kf2; s1.nhm = p.n / 2; s1.ncR2 = cRn; s1.nldg = p.M;
         s1.nalpha = p.alpha_c; s1.nsprime = p.shift_c + 0.5 * cUN;
         s1.tab = tab1; s1.Rfp = Rfp1; s1.nKfp = nKfp;
+        s1.kmax = kmax_dev; s1.ntile = fd.ntile; kmax_dev += 2 * fd.ntile;
         s1.sm_slots = slots_dev; s1.skew_cycles = (long long)((Kf1 + FBK - 1) / FBK) * SKEW_CYCLES_PER_KTILE;
         s1.tiles_r = (s1.Rf + FBR - 1) / FBR; s1.tiles_c = (Kf2 + FBC / 2 - 1) / (FBC / 2);
         if (s1.tiles_r * s1.tiles_c > max_t1) max_t1 = s1.tiles_r * s1.tiles_c;
@@ -500,7 +540,7 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
         s2.alpha = p.alpha_c; s2.oprime = p.off_c - 0.5 * cRn; s2.sprime = p.shift_c + 0.5 * cUN;
         s2.scale = scale; s2.sgn = sgn;
         s2.nKf = 0; s2.nhm = 0; s2.ncR2 = 0; s2.nldg = 0; s2.nalpha = 0.0; s2.nsprime = 0.0;
-        s2.tab = tab2; s2.Rfp = Rfp2; s2.nKfp = 0;
+        s2.tab = tab2; s2.Rfp = Rfp2; s2.nKfp = 0; s2.kmax = nullptr; s2.ntile = 0;
         s2.sm_slots = slots_dev + 256; s2.skew_cycles = (long long)((Kf2 + FBK - 1) / FBK) * SKEW_CYCLES_PER_KTILE;
         s2.tiles_r = (s2.Rf + FBR - 1) / FBR; s2.tiles_c = (s2.C + FBC - 1) / FBC;
         if (s2.tiles_r * s2.tiles_c > max_t2) max_t2 = s2.tiles_r * s2.tiles_c;
