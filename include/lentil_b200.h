@@ -81,6 +81,21 @@ int lfd_mft_c128_batched(const lfd_mft_desc *descs_host, int count,
 int lfd_mft_c128(const lfd_mft_desc *desc_host, void *workspace_dev, size_t workspace_bytes,
                  void *stream);
 
+/* Fused K1 + K2a (folded variant only): the input of plane i is not read from desc.f but formed on the
+ * fly as amp * mask * exp(+2 pi i opd / wavelength) over the m x n window at (r0, c0) of the pupil
+ * arrays (lentil/plane.py:502-507), so phasors never exist in HBM.  With intensity_out != 0 the result
+ * written to desc.out is |F|^2 as float64 (ldo in doubles) instead of the complex field — valid when
+ * the plane is the only Field of its wavefront (no coherent merge, lentil/field.py:413-461).
+ * Workspace: lfd_mft_workspace_bytes with the folded variant selected. */
+typedef struct lfd_pupil_src {
+    const double  *amp, *opd;     /* dev, n_r x n_c float64                                   */
+    const uint8_t *mask;          /* dev, this segment's n_r x n_c mask plane, or NULL         */
+    int32_t        n_r, n_c, r0, c0;
+    double         wavelength;
+} lfd_pupil_src;
+int lfd_mft_c128_from_pupil(const lfd_mft_desc *descs_host, const lfd_pupil_src *src_host, int count,
+                            int intensity_out, void *workspace_dev, size_t workspace_bytes, void *stream);
+
 /* ---- K2b: the same transform with complex64 in/out, 3xTF32 split precision on tcgen05 -------
  * Same descriptor, but `f` and `out` are complex64 (interleaved floats).  Every real product is
  * evaluated as hi*hi + hi*lo + lo*hi in TF32 with fp32 accumulation in TMEM; peak-normalised error
@@ -132,7 +147,8 @@ typedef struct lfd_window {
     int32_t     r0, c0;  /* position of E[0,0] in the output image (may be negative/clipped) */
     int32_t     group;   /* windows with equal group are summed coherently; groups must be
                             contiguous and non-decreasing in the array                    */
-    int32_t     c64;     /* 0: E is complex128; 1: E is complex64 (output of the K2b path)   */
+    int32_t     c64;     /* 0: E is complex128; 1: E is complex64 (output of the K2b path);
+                            2: E is a float64 INTENSITY window (lfd_mft_c128_from_pupil, intensity_out) */
     double      weight;  /* weight of the group (taken from its first window)             */
 } lfd_window;
 

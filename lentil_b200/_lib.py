@@ -29,6 +29,15 @@ class MftDesc(C.Structure):
     ]
 
 
+class PupilSrc(C.Structure):
+    """struct lfd_pupil_src"""
+    _fields_ = [
+        ("amp", C.c_void_p), ("opd", C.c_void_p), ("mask", C.c_void_p),
+        ("n_r", C.c_int32), ("n_c", C.c_int32), ("r0", C.c_int32), ("c0", C.c_int32),
+        ("wavelength", C.c_double),
+    ]
+
+
 class Segment(C.Structure):
     """struct lfd_segment"""
     _fields_ = [
@@ -58,6 +67,8 @@ SIGNATURES = {
     "lfd_mft_workspace_bytes": (C.c_size_t, [C.POINTER(MftDesc), C.c_int]),
     "lfd_mft_c128_batched": (C.c_int, [C.POINTER(MftDesc), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "lfd_mft_c128": (C.c_int, [C.POINTER(MftDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "lfd_mft_c128_from_pupil": (C.c_int, [C.POINTER(MftDesc), C.POINTER(PupilSrc), C.c_int, C.c_int, C.c_void_p,
+                                          C.c_size_t, C.c_void_p]),
     "lfd_mft_c64x3_workspace_bytes": (C.c_size_t, [C.POINTER(MftDesc), C.c_int]),
     "lfd_mft_c64x3_batched": (C.c_int, [C.POINTER(MftDesc), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "lfd_pupil_prep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,

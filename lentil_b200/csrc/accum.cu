@@ -50,7 +50,11 @@ accum_kernel(const lfd_window *__restrict__ wins, int nwin, double *__restrict__
             int rr = r - w.r0, cc = c - w.c0;
             if (rr >= 0 && rr < w.h && cc >= 0 && cc < w.w) {
                 double2 e;
-                if (w.c64) {
+                if (w.c64 == 2) {
+                    // float64 intensity window: a wavefront with a single Field, already squared by the MFT epilogue
+                    acc_r += w.weight * reinterpret_cast<const double *>(w.E)[(long long)rr * w.ld + cc];
+                    continue;
+                } else if (w.c64) {
                     const float2 f = reinterpret_cast<const float2 *>(w.E)[(long long)rr * w.ld + cc];
                     e = make_double2((double)f.x, (double)f.y);
                 } else {

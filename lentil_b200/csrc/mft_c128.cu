@@ -184,7 +184,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 // mft_folded.cu
 size_t folded_workspace_bytes(const lfd_mft_desc *descs, int count);
 int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, size_t workspace_bytes,
-                      cudaStream_t stream);
+                      cudaStream_t stream, const lfd_pupil_src *src, int intensity_out);
 
 static std::atomic<int> g_variant{LFD_MFT_FOLDED};
 
@@ -214,7 +214,7 @@ extern "C" int lfd_mft_c128_batched(const lfd_mft_desc *descs, int count, void *
     LFD_REQUIRE(descs != nullptr && count > 0, "lfd_mft_c128_batched: bad descriptor array");
     LFD_REQUIRE(workspace != nullptr, "lfd_mft_c128_batched: workspace is NULL");
     if (g_variant.load() == LFD_MFT_FOLDED)
-        return launch_mft_folded(descs, count, workspace, workspace_bytes, stream);
+        return launch_mft_folded(descs, count, workspace, workspace_bytes, stream, nullptr, 0);
     size_t need = lfd_mft_workspace_bytes(descs, count);
     LFD_REQUIRE(workspace_bytes >= need, "lfd_mft_c128_batched: workspace too small (%zu < %zu)",
                 workspace_bytes, need);

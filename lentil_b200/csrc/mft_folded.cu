@@ -59,7 +59,25 @@ struct FoldDesc {
     // tile: r2 = c - nhm  or  nhm - c - ncR2)
     int *kmax;
     int nhm, ncR2, ntile, pad2_;
+    // fused pupil prep (K1 inside the fold): when amp != NULL the input element (i, c) is not read from D
+    // but formed as amp * mask * exp(+2 pi i opd / lambda) at pupil pixel (pr0 + i, pc0 + c), lentil/plane.py:502-507
+    const double *amp, *opd;
+    const unsigned char *mask;   // this segment's mask plane, or NULL
+    long long pld;               // pupil row stride (n_c)
+    int pr0, pc0;
+    double wavelength;
 };
+
+__device__ __forceinline__ double2 pupil_phasor(const FoldDesc &d, int i, int c) {
+    const long long pix = (long long)(d.pr0 + i) * d.pld + (d.pc0 + c);
+    double a = d.amp[pix];
+    if (d.mask != nullptr && d.mask[pix] == 0) a = 0.0;
+    if (a == 0.0) return make_double2(0.0, 0.0);
+    const double tcyc = d.opd[pix] / d.wavelength;      // phase in cycles, reduced exactly
+    double sn, cs;
+    sincospi(2.0 * (tcyc - rint(tcyc)), &sn, &cs);
+    return make_double2(a * cs, a * sn);
+}
 
 struct FStageDesc {
     const double2 *G;   // ge at G, go at G + Kf*C   (Kf x C each, ld = C)
@@ -76,7 +94,8 @@ struct FStageDesc {
     const double2 *tab;
     int Rfp, nKfp;
     const int *kmax;    // row stage only: K rows that actually hold data, per column tile (NULL: all)
-    int ntile, pad3_;
+    int ntile;
+    int intensity;      // column stage: write |F|^2 as float64 (ld = ldo) instead of the complex field
     // de-phasing of the two CTAs that share an SM (see mft_folded_kernel): per-launch slot counters
     // (one per SM, zeroed with the descriptor upload) and the skew in cycles (~ half a tile)
     unsigned *sm_slots;
@@ -155,8 +174,14 @@ fold_kernel(const FoldDesc *__restrict__ descs) {
     for (int t = threadIdx.x; t < d.ntile; t += blockDim.x) tile_nz[t] = 0;
     __syncthreads();
     for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
-        double2 a = has_p ? rowp[c] : make_double2(0.0, 0.0);
-        double2 b = center ? make_double2(0.0, 0.0) : rowm[c];
+        double2 a, b;
+        if (d.amp != nullptr) {
+            a = has_p ? pupil_phasor(d, ip, c) : make_double2(0.0, 0.0);
+            b = center ? make_double2(0.0, 0.0) : pupil_phasor(d, im, c);
+        } else {
+            a = has_p ? rowp[c] : make_double2(0.0, 0.0);
+            b = center ? make_double2(0.0, 0.0) : rowm[c];
+        }
         double2 gp = make_double2(a.x * pc - a.y * ps, a.x * ps + a.y * pc);
         if (center) {
             ge[c] = gp;
@@ -379,6 +404,14 @@ mft_folded_kernel(const FStageDesc *__restrict__ descs) {
                     if (c >= d.C) continue;
                     const double Ar = accA[mb][q][0][i], Ai = accA[mb][q][1][i];
                     const double Br = d.sgn * accB[mb][q][0][i], Bi = d.sgn * accB[mb][q][1][i];
+                    if (d.intensity) {
+                        // |post| = scale, so |F|^2 = scale^2 |A +- i sgn B|^2: no phase needed
+                        double *icol = reinterpret_cast<double *>(d.O) + (long long)c * d.ldo;
+                        const double s2 = ppc * ppc + pps * pps;
+                        if (has_p) { const double xr = Ar - Bi, xi = Ai + Br; icol[kp] = s2 * (xr * xr + xi * xi); }
+                        if (has_m) { const double xr = Ar + Bi, xi = Ai - Br; icol[km] = s2 * (xr * xr + xi * xi); }
+                        continue;
+                    }
                     double2 *col = d.O + (long long)c * d.ldo;
                     if (has_p) {   // A + i sgn B
                         double xr = Ar - Bi, xi = Ai + Br;
@@ -459,7 +492,7 @@ size_t folded_workspace_bytes(const lfd_mft_desc *descs, int count) {
 }
 
 int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, size_t workspace_bytes,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, const lfd_pupil_src *src = nullptr, int intensity_out = 0) {
     size_t need = folded_workspace_bytes(descs, count);
     LFD_REQUIRE(workspace_bytes >= need, "lfd_mft_c128_batched: workspace too small (%zu < %zu)",
                 workspace_bytes, need);
@@ -487,7 +520,10 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
     int max_rows = 0, max_t1 = 0, max_t2 = 0, max_tab = 0;
     for (int i = 0; i < count; ++i) {
         const lfd_mft_desc &p = descs[i];
-        if (!(p.m > 0 && p.n > 0 && p.M > 0 && p.N > 0 && p.ldf >= p.n && p.ldo >= p.N && p.f && p.out)) {
+        if (!(p.m > 0 && p.n > 0 && p.M > 0 && p.N > 0 && p.ldo >= p.N && p.out &&
+              (src ? (src[i].amp && src[i].opd && src[i].wavelength != 0.0 && src[i].r0 >= 0 && src[i].c0 >= 0 &&
+                      src[i].r0 + p.m <= src[i].n_r && src[i].c0 + p.n <= src[i].n_c)
+                   : (p.f && p.ldf >= p.n)))) {
             free(h);
             LFD_REQUIRE(false, "lfd_mft_c128_batched: plane %d has invalid shape/ld/pointers", i);
         }
@@ -512,6 +548,13 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
         fd.D = (const double2 *)p.f; fd.ldd = p.ldf; fd.G = G1;
         fd.K = p.m; fd.C = p.n; fd.Kf = Kf1; fd.hm = p.m / 2; fd.cR2 = cRm; fd.pad_ = 0;
         fd.alpha = p.alpha_r; fd.sprime = p.shift_r + 0.5 * cUM; fd.sgn = sgn;
+        if (src) {
+            fd.D = nullptr; fd.ldd = 0;
+            fd.amp = src[i].amp; fd.opd = src[i].opd; fd.mask = src[i].mask;
+            fd.pld = src[i].n_c; fd.pr0 = src[i].r0; fd.pc0 = src[i].c0; fd.wavelength = src[i].wavelength;
+        } else {
+            fd.amp = nullptr; fd.opd = nullptr; fd.mask = nullptr; fd.pld = 0; fd.pr0 = fd.pc0 = 0; fd.wavelength = 1.0;
+        }
         fd.nhm = p.n / 2; fd.ncR2 = cRn; fd.ntile = (Kf2 + FBC / 2 - 1) / (FBC / 2); fd.pad2_ = 0;
         fd.kmax = kmax_dev;
         if (fd.ntile > FOLD_MAX_TILES) { free(h); LFD_REQUIRE(false, "lfd_mft_c128_batched: plane %d is too wide (%d columns)", i, p.n); }
@@ -540,7 +583,7 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
         s2.alpha = p.alpha_c; s2.oprime = p.off_c - 0.5 * cRn; s2.sprime = p.shift_c + 0.5 * cUN;
         s2.scale = scale; s2.sgn = sgn;
         s2.nKf = 0; s2.nhm = 0; s2.ncR2 = 0; s2.nldg = 0; s2.nalpha = 0.0; s2.nsprime = 0.0;
-        s2.tab = tab2; s2.Rfp = Rfp2; s2.nKfp = 0; s2.kmax = nullptr; s2.ntile = 0;
+        s2.tab = tab2; s2.Rfp = Rfp2; s2.nKfp = 0; s2.kmax = nullptr; s2.ntile = 0; s2.intensity = intensity_out; s1.intensity = 0;
         s2.sm_slots = slots_dev + 256; s2.skew_cycles = (long long)((Kf2 + FBK - 1) / FBK) * SKEW_CYCLES_PER_KTILE;
         s2.tiles_r = (s2.Rf + FBR - 1) / FBR; s2.tiles_c = (s2.C + FBC - 1) / FBC;
         if (s2.tiles_r * s2.tiles_c > max_t2) max_t2 = s2.tiles_r * s2.tiles_c;
@@ -569,3 +612,10 @@ extern "C" int lfd_debug_tile_timing(long long *buf_dev) {
     return (int)cudaMemcpyToSymbol(lfd::g_tile_timing, &buf_dev, sizeof(buf_dev));
 }
 #endif
+
+extern "C" int lfd_mft_c128_from_pupil(const lfd_mft_desc *descs, const lfd_pupil_src *src, int count,
+                                       int intensity_out, void *workspace, size_t workspace_bytes, void *stream) {
+    if (count == 0) return 0;
+    LFD_REQUIRE(descs && src && workspace && count > 0, "lfd_mft_c128_from_pupil: bad arguments");
+    return lfd::launch_mft_folded(descs, count, workspace, workspace_bytes, (cudaStream_t)stream, src, intensity_out);
+}

@@ -57,9 +57,10 @@ def mft_flops_executed(descs, count):
     return tot
 
 
-def run_mft(descs, count, precision='c128'):
+def run_mft(descs, count, precision='c128', pupil_src=None, intensity_out=False):
     """Launch a batch of planes on the current stream with a torch-owned workspace.
-    precision 'c128': K2a (FP64 DMMA); 'c64': K2b (complex64 arrays, 3xTF32 on tcgen05)."""
+    precision 'c128': K2a (FP64 DMMA); 'c64': K2b (complex64 arrays, 3xTF32 on tcgen05).
+    pupil_src: optional lfd_pupil_src table — the fused K1+K2a entry point (folded variant, c128)."""
     L = _lib.lib()
     if precision == 'c64':
         need = L.lfd_mft_c64x3_workspace_bytes(descs, count)
@@ -73,8 +74,12 @@ def run_mft(descs, count, precision='c128'):
         import torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    _lib.check(L.lfd_mft_c128_batched(descs, count, ws.data_ptr(), need, device.stream_ptr()),
-               "lfd_mft_c128_batched")
+    if pupil_src is not None:
+        _lib.check(L.lfd_mft_c128_from_pupil(descs, pupil_src, count, int(bool(intensity_out)), ws.data_ptr(), need,
+                                             device.stream_ptr()), "lfd_mft_c128_from_pupil")
+    else:
+        _lib.check(L.lfd_mft_c128_batched(descs, count, ws.data_ptr(), need, device.stream_ptr()),
+                   "lfd_mft_c128_batched")
     if TIMERS is not None:
         e1.record()
         TIMERS.append((e0, e1, mft_flops(descs, count), mft_flops_executed(descs, count)))

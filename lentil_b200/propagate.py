@@ -240,11 +240,17 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
         cr, cl = wf_r[c0:c0 + step], wf_l[c0:c0 + step]
         lam = wavelengths[cl]
         nw = len(lam)
-        phasors = torch.empty(nw, ops['total'], dtype=cdtype, device=device.device())
-        for r in np.unique(cr):                                            # K1, one launch per realisation
-            sel = np.flatnonzero(cr == r)
-            plane._phasors_into(phasors[int(sel[0]):int(sel[-1]) + 1], lam[sel], ops,
-                                None if opd_stack is None else opd_stack[int(r)])
+        # With one field point every phasor feeds exactly one transform: K1 is then fused into the fold
+        # kernel of the folded K2a (lfd_mft_c128_from_pupil) and phasors never exist in HBM; with a single
+        # segment the column stage also squares the field itself (no coherent merge to do in K3).
+        fused = (not c64) and P == 1 and _lib.lib().lfd_get_mft_variant() == 1
+        intensity_out = fused and nseg == 1
+        if not fused:
+            phasors = torch.empty(nw, ops['total'], dtype=cdtype, device=device.device())
+            for r in np.unique(cr):                                        # K1, one launch per realisation
+                sel = np.flatnonzero(cr == r)
+                plane._phasors_into(phasors[int(sel[0]):int(sel[-1]) + 1], lam[sel], ops,
+                                    None if opd_stack is None else opd_stack[int(r)])
         # ---- window planning: rows (wavefront, p, n) -> window shape / offset / dft shift ----------
         if static:
             plans = [plan_window(_shift_for(tl, z, lam[0], du, oversample), prop_shape_out, out_extent)
@@ -274,12 +280,28 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
             continue
         sizes = jshape[:, 0] * jshape[:, 1]
         pos = np.concatenate(([0], np.cumsum(sizes)[:-1]))
-        buf = torch.empty(int(sizes.sum()), dtype=cdtype, device=device.device())
+        osize = 8 if intensity_out else esize
+        buf = torch.empty(int(sizes.sum()), dtype=torch.float64 if intensity_out else cdtype, device=device.device())
         # ---- K2a / K2b descriptors, one row per plane -------------------------------------------------
         D = np.zeros(nj, dtype=np.dtype(_lib.MftDesc))
-        D['f'] = phasors.data_ptr() + esize * (jw * ops['total'] + seg_off[jn])
+        src = None
+        if fused:
+            n_r, n_c = ops['shape']
+            seg_r0 = np.array([segs[n].r0 for n in range(nseg)], dtype=np.int64)
+            seg_c0 = np.array([segs[n].c0 for n in range(nseg)], dtype=np.int64)
+            seg_mi = np.array([segs[n].mask_index for n in range(nseg)], dtype=np.int64)
+            src = np.zeros(nj, dtype=np.dtype(_lib.PupilSrc))
+            src['amp'] = ops['amp'].data_ptr()
+            src['opd'] = (ops['opd'].data_ptr() if opd_stack is None
+                          else opd_stack.data_ptr() + 8 * n_r * n_c * cr[jw])
+            src['mask'] = 0 if ops['mask'] is None else ops['mask'].data_ptr() + n_r * n_c * seg_mi[jn]
+            src['n_r'], src['n_c'] = n_r, n_c
+            src['r0'], src['c0'] = seg_r0[jn], seg_c0[jn]
+            src['wavelength'] = lam[jw]
+        else:
+            D['f'] = phasors.data_ptr() + esize * (jw * ops['total'] + seg_off[jn])
         D['ldf'] = seg_w[jn]
-        D['out'] = buf.data_ptr() + esize * pos
+        D['out'] = buf.data_ptr() + osize * pos
         D['ldo'] = jshape[:, 1]
         D['m'], D['n'] = seg_h[jn], seg_w[jn]
         D['M'], D['N'] = jshape[:, 0], jshape[:, 1]
@@ -290,7 +312,9 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
         D['unitary'] = 1
         for b0 in range(0, nj, _MAX_PLANES_PER_LAUNCH):                      # K2a
             nb = min(_MAX_PLANES_PER_LAUNCH, nj - b0)
-            _fourier.run_mft(D[b0:b0 + nb].ctypes.data_as(C.POINTER(_lib.MftDesc)), nb, precision)
+            _fourier.run_mft(D[b0:b0 + nb].ctypes.data_as(C.POINTER(_lib.MftDesc)), nb, precision,
+                             None if src is None else src[b0:b0 + nb].ctypes.data_as(C.POINTER(_lib.PupilSrc)),
+                             intensity_out)
         # ---- K3: per output image (realisation, field point); groups = wavefronts --------------------
         Wn = np.zeros(nj, dtype=np.dtype(_lib.Window))
         Wn['E'], Wn['ld'] = D['out'], jshape[:, 1]
@@ -298,7 +322,7 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
         Wn['r0'] = H // 2 - jshape[:, 0] // 2 + jshift[:, 0]      # lentil/field.py:267-268
         Wn['c0'] = W // 2 - jshape[:, 1] // 2 + jshift[:, 1]
         Wn['group'] = jw
-        Wn['c64'] = 1 if c64 else 0
+        Wn['c64'] = 2 if intensity_out else (1 if c64 else 0)
         Wn['weight'] = weights[cl][jw]
         img = cr[jw] * P + jp
         for im in np.unique(img):
