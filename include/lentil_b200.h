@@ -194,6 +194,14 @@ int lfd_remove_tilt(const double *opd_dev, const uint8_t *mask_dev, const double
 int lfd_mask_bbox(const void *x_dev, int32_t is_f64, int32_t nonzero, int32_t n_r, int32_t n_c,
                   int32_t nplanes, int32_t *out_dev /* 4 x nplanes */, void *stream);
 
+/* ---- detector-side sampling of the oversampled PSF -----------------
+ * lfd_rebin: out[r,c] = sum of the factor x factor block of img — lentil/util.py:221-258 (rebin).
+ * lfd_scale_separable: F[r,c] *= my[r]*mx[c] (complex128, in place) — the pixel-MTF multiply of
+ *   lentil/detector.py:213-220 (pixel); lfd_abs_c128: out = |F| (detector.py:220). */
+int lfd_rebin(const double *img_dev, int64_t ld, int32_t h, int32_t w, int32_t factor, double *out_dev, void *stream);
+int lfd_scale_separable(void *F_dev, int64_t ld, int32_t h, int32_t w, const double *my_dev, const double *mx_dev, void *stream);
+int lfd_abs_c128(const void *F_dev, int64_t ld, int32_t h, int32_t w, double *out_dev, void *stream);
+
 /* ---- host-buffer convenience layer (what bench.py's e2e leg and the numpy shim call) ------
  * A context owns a device workspace, pinned staging buffers and one stream on `device`.
  */

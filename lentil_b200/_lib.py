@@ -88,6 +88,9 @@ SIGNATURES = {
     "lfd_remove_tilt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double,
                                   C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "lfd_mask_bbox": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "lfd_rebin": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "lfd_scale_separable": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lfd_abs_c128": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "lfd_ctx_create": (C.c_void_p, [C.c_int]),
     "lfd_ctx_destroy": (None, [C.c_void_p]),
     "lfd_ctx_dft2_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,

@@ -1,0 +1,85 @@
+// Detector-side sampling of an oversampled PSF — the step that follows
+// the PSF accumulation in every lentil example (docs/examples/simple.rst:62-64).
+//
+//  * lfd_rebin            : integer-factor binning, lentil/util.py:221-258 (rebin: reshape + sum)
+//  * lfd_scale_separable  : F[r,c] *= my[r] * mx[c] for a complex field — the pixel-MTF multiply of
+//                           lentil/detector.py:213-220 (pixel): fft2(img) * outer(sinc, sinc); the two
+//                           transforms around it are K2a launches (dft2 with alpha = 1/n is the FFT).
+//  * lfd_abs_c128         : |z| of a complex field into float64 (detector.py:220, np.abs(ifft2(...)))
+// All three are HBM-bound element-wise kernels.
+#include "lfd_common.cuh"
+
+namespace lfd {
+
+__global__ void __launch_bounds__(256)
+rebin_kernel(const double *__restrict__ img, long long ld, int factor, double *__restrict__ out, int oh, int ow) {
+    const long long n = (long long)oh * ow;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e / ow), c = (int)(e % ow);
+        const double *p = img + (long long)r * factor * ld + (long long)c * factor;
+        double s = 0.0;
+        // same association as numpy's .sum(-1).sum(1): inner (column) sums first, then over the rows
+        for (int i = 0; i < factor; ++i) {
+            double row = 0.0;
+            for (int j = 0; j < factor; ++j) row += p[(long long)i * ld + j];
+            s += row;
+        }
+        out[e] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+scale_separable_kernel(double2 *__restrict__ F, long long ld, int h, int w, const double *__restrict__ my,
+                       const double *__restrict__ mx) {
+    const long long n = (long long)h * w;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e / w), c = (int)(e % w);
+        const double k = my[r] * mx[c];
+        double2 v = F[(long long)r * ld + c];
+        F[(long long)r * ld + c] = make_double2(v.x * k, v.y * k);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+abs_c128_kernel(const double2 *__restrict__ F, long long ld, int h, int w, double *__restrict__ out) {
+    const long long n = (long long)h * w;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e / w), c = (int)(e % w);
+        const double2 v = F[(long long)r * ld + c];
+        out[e] = hypot(v.x, v.y);
+    }
+}
+
+static inline unsigned grid_for(long long n) {
+    long long b = (n + 255) / 256;
+    return (unsigned)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
+}
+
+}  // namespace lfd
+
+using namespace lfd;
+
+extern "C" int lfd_rebin(const double *img, int64_t ld, int32_t h, int32_t w, int32_t factor, double *out, void *stream) {
+    LFD_REQUIRE(img && out && factor > 0 && h >= factor && w >= factor && ld >= w, "lfd_rebin: bad arguments");
+    const int oh = h / factor, ow = w / factor;
+    rebin_kernel<<<grid_for((long long)oh * ow), 256, 0, (cudaStream_t)stream>>>(img, ld, factor, out, oh, ow);
+    LFD_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+extern "C" int lfd_scale_separable(void *F, int64_t ld, int32_t h, int32_t w, const double *my, const double *mx, void *stream) {
+    LFD_REQUIRE(F && my && mx && h > 0 && w > 0 && ld >= w, "lfd_scale_separable: bad arguments");
+    scale_separable_kernel<<<grid_for((long long)h * w), 256, 0, (cudaStream_t)stream>>>((double2 *)F, ld, h, w, my, mx);
+    LFD_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+extern "C" int lfd_abs_c128(const void *F, int64_t ld, int32_t h, int32_t w, double *out, void *stream) {
+    LFD_REQUIRE(F && out && h > 0 && w > 0 && ld >= w, "lfd_abs_c128: bad arguments");
+    abs_c128_kernel<<<grid_for((long long)h * w), 256, 0, (cudaStream_t)stream>>>((const double2 *)F, ld, h, w, out);
+    LFD_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}

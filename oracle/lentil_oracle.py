@@ -417,3 +417,27 @@ def psf(amplitude, opd, mask, wavelengths, weights, dx, z, pixelscale, shape, pr
         w2, _ = propagate_dft(w1, wl, dx, z, pixelscale, shape, prop_shape, oversample, out_mask)
         img = wavefront_insert(w2, img, wt)
     return img
+
+
+# --------------------------------------------------------------------------------------------
+# detector-side sampling (next rows): lentil/util.py:221-258, lentil/detector.py:167-220
+# --------------------------------------------------------------------------------------------
+
+
+def rebin(img, factor):
+    """Integer-factor binning by reshape + sum, lentil/util.py:221-258."""
+    img = np.asarray(img)
+    if np.iscomplexobj(img):
+        raise ValueError('rebin is not defined for complex data')
+    if img.ndim == 3:
+        return np.stack([rebin(plane, factor) for plane in img])
+    return img.reshape(img.shape[0] // factor, factor, img.shape[1] // factor, factor).sum(-1).sum(1)
+
+
+def pixel(img, oversample=1):
+    """Square-pixel MTF applied in the Fourier domain, lentil/detector.py:213-220."""
+    img = np.asarray(img)
+    mtf_x = np.sinc(np.fft.fftfreq(img.shape[1]) * oversample)
+    mtf_y = np.sinc(np.fft.fftfreq(img.shape[0]) * oversample)
+    kernel = np.dot(mtf_x[:, np.newaxis], mtf_y[np.newaxis, :])
+    return np.abs(np.fft.ifft2(np.fft.fft2(img) * kernel))

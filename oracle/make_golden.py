@@ -284,11 +284,23 @@ def golden_propagate():
           "(monolithic+tilt, 3-segment fit_tilt with prop_shape, detector mask, off-detector)")
 
 
+def golden_detector():
+    rng = np.random.default_rng(77)
+    img, cube = rng.random((48, 48)), rng.random((3, 30, 42))
+    d = dict(img=img, cube=cube, rebin3=lentil.rebin(img, 3), rebin_cube2=lentil.rebin(cube, 2),
+             pixel2=lentil.detector.pixel(img, 2), pixel3=lentil.detector.pixel(img[:45, :45], 3))
+    assert np.array_equal(oc.rebin(img, 3), d["rebin3"]) and np.array_equal(oc.rebin(cube, 2), d["rebin_cube2"])
+    assert np.array_equal(oc.pixel(img, 2), d["pixel2"]) and np.array_equal(oc.pixel(img[:45, :45], 3), d["pixel3"])
+    np.savez_compressed(os.path.join(GOLD, "detector.npz"), **d)
+    print("detector: oracle == reference bit-for-bit (rebin 2-D / cube, pixel MTF even / odd size)")
+
+
 if __name__ == "__main__":
     assert lentil.__version__ == "0.8.8", lentil.__version__
     golden_dft2()
     golden_extent()
     golden_field()
     golden_propagate()
+    golden_detector()
     sizes = {f: os.path.getsize(os.path.join(GOLD, f)) for f in sorted(os.listdir(GOLD))}
     print("fixtures:", sizes)

@@ -106,3 +106,11 @@ def test_propagate_golden(golden):
                            [tuple(t) for t in d["D_ptilt"]])
     pr, _ = oc.propagate_dft(ph, 650e-9, (1 / 56, 1 / 56), 10.0, 5e-6, (16, 16), None, 2)
     assert pr == []
+
+
+def test_detector_golden(golden):
+    d = golden("detector")
+    assert np.array_equal(oc.rebin(d["img"], 3), d["rebin3"])
+    assert np.array_equal(oc.rebin(d["cube"], 2), d["rebin_cube2"])
+    assert np.array_equal(oc.pixel(d["img"], 2), d["pixel2"])
+    assert np.array_equal(oc.pixel(d["img"][:45, :45], 3), d["pixel3"])
