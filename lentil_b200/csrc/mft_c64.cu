@@ -73,7 +73,8 @@ struct CStage {
     // outputs
     float2 *out; long long ldo;            // final stage: complex64 M x N (row-major), written transposed
     unsigned char *nB; long long nplane;   // FOLD_OUT: next stage's pre-blocked data operand
-    int nKf, nKpad, nhm, ncR2, nKfp, pad_;
+    int nKf, nKpad, nhm, ncR2, nKfp, ntile;
+    const int *kmax;                       // row stage: support map of its input (NULL: all K blocks)
     double alpha, oprime, sprime, scale, nalpha, nsprime;
 };
 
@@ -181,6 +182,8 @@ struct FoldSplit {
     int permute;                     // 1: columns arranged as HALF (j+) + HALF (j-) per TN-slot tile for FOLD_OUT
     int nhm, ncR2, nKf, slots;       // slots = Npad / 2
     double alpha, sprime, sgn;
+    int *kmax;                       // support map, as in mft_folded.cu: [tile] = 1 + last row with data,
+    int ntile, pad_;                 // [ntile + tile] = Kf - first row with data (column tile = 32 slots)
 };
 
 __global__ void __launch_bounds__(256)
@@ -190,6 +193,8 @@ fold_split_kernel(const FoldSplit *__restrict__ descs) {
     if (r0 >= d.Kpad || s0 >= d.slots) return;
     __shared__ float tile[4][32][33];           // ge.re, ge.im, go.re, go.im  [r][slot]
     __shared__ float2 pre[32];
+    __shared__ int row_nz[32];
+    if (threadIdx.x < 32) row_nz[threadIdx.x] = 0;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
     if (threadIdx.x < 32) {
         double c, s;
@@ -217,17 +222,25 @@ fold_split_kernel(const FoldSplit *__restrict__ descs) {
             const float2 p = pre[rr];
             float2 a = (ip < d.K) ? d.D[(long long)ip * d.ldd + j] : make_float2(0.f, 0.f);
             const float gpr = a.x * p.x - a.y * p.y, gpi = a.x * p.y + a.y * p.x;
+            bool nz = (a.x != 0.f) || (a.y != 0.f);
             if (d.cR2 == 0 && r == 0) {
                 ger = gpr; gei = gpi;
             } else {
                 float2 b = d.D[(long long)im * d.ldd + j];
+                nz = nz || (b.x != 0.f) || (b.y != 0.f);
                 const float gmr = b.x * p.x + b.y * p.y, gmi = b.y * p.x - b.x * p.y;
                 ger = gpr + gmr; gei = gpi + gmi; gor = gpr - gmr; goi = gpi - gmi;
             }
+            if (nz) row_nz[rr] = 1;                 // benign race
         }
         tile[0][rr][tx] = ger; tile[1][rr][tx] = gei; tile[2][rr][tx] = gor; tile[3][rr][tx] = goi;
     }
     __syncthreads();
+    if (threadIdx.x < 32 && row_nz[threadIdx.x] && d.kmax != nullptr) {
+        const int r = r0 + threadIdx.x, tl = s0 / 32;
+        atomicMax(d.kmax + tl, r + 1);
+        atomicMax(d.kmax + d.ntile + tl, d.Kf - r);
+    }
     // this CUDA block owns one column tile (64 real columns) x 4 k-blocks = 4 x 8 KB of the pre-blocked
     // operand; consecutive threads write consecutive 16-byte chunks (4 K values of one real column)
     const int tileN = s0 / 32, nkb = d.Kpad / KB;
@@ -277,6 +290,14 @@ mft_c64_kernel(const CStage *__restrict__ descs) {
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nkb = d.Kpad / KB;
+    // k-block range that holds data for this column tile (support map of the fold kernel); at least one block
+    int kb0 = 0, kb1 = nkb;
+    if (FOLD_OUT && d.kmax != nullptr) {
+        const int last = min(d.Kf, d.kmax[tc]), first = max(0, d.Kf - d.kmax[d.ntile + tc]);
+        kb1 = min(nkb, (last + KB - 1) / KB);
+        kb0 = min(first / KB, kb1);
+        if (kb1 <= kb0) { kb0 = 0; kb1 = 1; }
+    }
 
     if (tid == 0) {
         for (int s = 0; s < NA; ++s) { mbar_init(&fullA_bar[s], NGEN / 32); mbar_init(&emptyA_bar[s], 1); }
@@ -298,17 +319,17 @@ mft_c64_kernel(const CStage *__restrict__ descs) {
         {
             TT_DECL
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NR >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % NA;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const int jb = kb - kb0, s = jb % NA;
                 TT_BEGIN
-                mbar_wait(&fullA_bar[s], (kb / NA) & 1);
+                mbar_wait(&fullA_bar[s], (jb / NA) & 1);
                 TT_ADD(tt_a)
-                mbar_wait(&fullB_bar[kb % NB], (kb / NB) & 1);
+                mbar_wait(&fullB_bar[jb % NB], (jb / NB) & 1);
                 TT_ADD(tt_b)
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint32_t sa = smem_u32(smem + (size_t)s * A_BYTES);
-                const uint32_t sb = smem_u32(smem + B_RING + (size_t)(kb % NB) * B_BYTES);
-                const uint32_t acc = kb > 0 ? 1u : 0u;
+                const uint32_t sb = smem_u32(smem + B_RING + (size_t)(jb % NB) * B_BYTES);
+                const uint32_t acc = jb > 0 ? 1u : 0u;
                 if (elect_one()) {
 #pragma unroll
                 for (int rt = 0; rt < 2; ++rt) {
@@ -327,7 +348,7 @@ mft_c64_kernel(const CStage *__restrict__ descs) {
                     umma_tf32(t0 + 3 * NR, sl, oh, idesc, 1u);       //         + sin_lo * go_hi
                 }
                 umma_commit(&emptyA_bar[s]);                // frees the twiddle stage and the data slot
-                umma_commit(&emptyB_bar[kb % NB]);          // when these MMAs retire
+                umma_commit(&emptyB_bar[jb % NB]);          // when these MMAs retire
                 }
                 __syncwarp();
                 TT_ADD(tt_c)
@@ -342,9 +363,9 @@ mft_c64_kernel(const CStage *__restrict__ descs) {
         // ================= data-operand producer: one bulk copy per k-block =================
         if (lane == 0) {
             const unsigned char *src = d.B + (long long)tc * nkb * B_BYTES;
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int sl = kb % NB;
-                if (kb >= NB) mbar_wait(&emptyB_bar[sl], ((kb / NB) - 1) & 1);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const int jb = kb - kb0, sl = jb % NB;
+                if (jb >= NB) mbar_wait(&emptyB_bar[sl], ((jb / NB) - 1) & 1);
                 const uint32_t bar = smem_u32(&fullB_bar[sl]);
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)B_BYTES) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -367,11 +388,13 @@ mft_c64_kernel(const CStage *__restrict__ descs) {
         const uint32_t adst = (g >> 3) * SBO + (g & 7) * 32;    // row g of a 256-row twiddle plane
         const uint32_t swz = ((g >> 2) & 1) << 4;
         TT_DECL
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % NA;
+        if (kb0 > 0)   // late start: seed the carried twiddle at the first K block that is processed
+            cis_cycles(d.alpha, (double)(kb0 * KB) + 0.5 * d.cR2, (double)u + 0.5 * d.cU2, 1.0, Wc, Ws);
+        for (int kb = kb0; kb < kb1; ++kb) {
+            const int jb = kb - kb0, s = jb % NA;
             TT_BEGIN
             // the twiddle stage must be free before it is overwritten
-            if (kb >= NA) mbar_wait(&emptyA_bar[s], ((kb / NA) - 1) & 1);
+            if (jb >= NA) mbar_wait(&emptyA_bar[s], ((jb / NA) - 1) & 1);
             TT_ADD(tt_a)
             // twiddles of this row for the 8 K of the block
             {
@@ -543,8 +566,14 @@ static Geo geo(const lfd_mft_desc &p) {
 }
 static size_t table_bytes(int Rfp, int nKfp) { return al((size_t)4 * Rfp * sizeof(double2)) + al(((size_t)8 * Rfp + nKfp) * sizeof(float2)); }
 
+static size_t kmax_ints(const lfd_mft_desc *descs, int count) {
+    size_t n = 0;
+    for (int i = 0; i < count; ++i) n += 2 * (size_t)(geo(descs[i]).slots1 / TN);
+    return n;
+}
+
 size_t c64_workspace_bytes(const lfd_mft_desc *descs, int count) {
-    size_t bytes = al((size_t)count * (sizeof(FoldSplit) + 2 * sizeof(CStage)));
+    size_t bytes = al((size_t)count * (sizeof(FoldSplit) + 2 * sizeof(CStage)) + kmax_ints(descs, count) * sizeof(int));
     for (int i = 0; i < count; ++i) {
         Geo g = geo(descs[i]);
         bytes += al((size_t)4 * g.Npad1 * g.Kpad1 * sizeof(float));
@@ -567,7 +596,9 @@ int launch_mft_c64(const lfd_mft_desc *descs, int count, void *workspace, size_t
         LFD_CUDA_OK(cudaFuncSetAttribute(mft_c64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         attr_set = true;
     }
-    const size_t hdr = (size_t)count * (sizeof(FoldSplit) + 2 * sizeof(CStage));
+    const size_t desc_bytes = (size_t)count * (sizeof(FoldSplit) + 2 * sizeof(CStage));
+    const size_t hdr = desc_bytes + kmax_ints(descs, count) * sizeof(int);     // support maps start at zero
+    int *kmax_dev = (int *)((char *)workspace + desc_bytes);
     char *h = (char *)calloc(hdr, 1);
     LFD_REQUIRE(h != nullptr, "out of host memory");
     FoldSplit *hf = (FoldSplit *)h;
@@ -603,6 +634,7 @@ int launch_mft_c64(const lfd_mft_desc *descs, int count, void *workspace, size_t
         f.K = p.m; f.C = p.n; f.Kf = g.Kf1; f.Kpad = g.Kpad1; f.hm = p.m / 2; f.cR2 = cRm;
         f.permute = 1; f.nhm = p.n / 2; f.ncR2 = cRn; f.nKf = g.Kf2; f.slots = g.slots1;
         f.alpha = p.alpha_r; f.sprime = p.shift_r + 0.5 * cUM; f.sgn = sgn;
+        f.kmax = kmax_dev; f.ntile = g.slots1 / TN; f.pad_ = 0;
         if (g.slots1 / 32 > max_fs_x) max_fs_x = g.slots1 / 32;
         if (g.Kpad1 / 32 > max_fs_y) max_fs_y = g.Kpad1 / 32;
 
@@ -615,6 +647,7 @@ int launch_mft_c64(const lfd_mft_desc *descs, int count, void *workspace, size_t
         s1.nKf = g.Kf2; s1.nKpad = g.Kpad2; s1.nhm = p.n / 2; s1.ncR2 = cRn; s1.nKfp = g.nKfp;
         s1.alpha = p.alpha_r; s1.oprime = p.off_r - 0.5 * cRm; s1.sprime = p.shift_r + 0.5 * cUM; s1.scale = 1.0;
         s1.nalpha = p.alpha_c; s1.nsprime = p.shift_c + 0.5 * cUN;
+        s1.kmax = kmax_dev; s1.ntile = f.ntile; kmax_dev += 2 * f.ntile;
         s1.scale *= 1.0 + TRUNC_LOSS_PER_PRODUCT * g.Kf1;
 
         CStage &s2 = hs[count + i];
@@ -625,7 +658,7 @@ int launch_mft_c64(const lfd_mft_desc *descs, int count, void *workspace, size_t
         s2.out = (float2 *)p.out; s2.ldo = p.ldo; s2.nB = nullptr; s2.nplane = 0;
         s2.nKf = 0; s2.nKpad = 0; s2.nhm = 0; s2.ncR2 = 0; s2.nKfp = 0;
         s2.alpha = p.alpha_c; s2.oprime = p.off_c - 0.5 * cRn; s2.sprime = p.shift_c + 0.5 * cUN; s2.scale = scale;
-        s2.nalpha = 0.0; s2.nsprime = 0.0;
+        s2.nalpha = 0.0; s2.nsprime = 0.0; s2.kmax = nullptr; s2.ntile = 0;
         s2.scale *= 1.0 + TRUNC_LOSS_PER_PRODUCT * g.Kf2;
 
         const int t1 = 12 * g.Rfp1 + g.nKfp, t2 = 12 * g.Rfp2;
