@@ -332,7 +332,8 @@ def run_ours(args):
         "traffic": traffic,
         "note": "achieved counts ALGORITHMIC flops, 8*M*n*(m+N) per plane (SURVEY.md 8d); the folded kernel "
                 "executes ~4x fewer (even/odd folding of both DFT axes -> real twiddles), so frac > 1 is the "
-                "algorithmic saving, not a timing artefact; executed_* is what the DMMA pipe really ran",
+                "algorithmic saving, not a timing artefact; executed_* is what the DMMA pipe ran (an upper bound: the "
+                "row stage also skips the K tiles its support map marks empty, ~21% of them for a disc)",
         "executed_tflops": executed,
         "executed_frac": executed / probe["dmma_tflops"] if executed else None,
         "peak_source": "measured in this run by lfd_probe_fp64 (register-resident DMMA.8x8x4 issue loop, all SMs); "
