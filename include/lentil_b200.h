@@ -202,6 +202,13 @@ int lfd_rebin(const double *img_dev, int64_t ld, int32_t h, int32_t w, int32_t f
 int lfd_scale_separable(void *F_dev, int64_t ld, int32_t h, int32_t w, const double *my_dev, const double *mx_dev, void *stream);
 int lfd_abs_c128(const void *F_dev, int64_t ld, int32_t h, int32_t w, double *out_dev, void *stream);
 
+/* OPD synthesis: out[r] = base + sum_k coeffs[r][k] * basis[k], the
+ * np.einsum('ijk,i->jk', basis, coeff) of docs/user/wavefront_error.rst:118-135 for R coefficient
+ * vectors at once.  basis: K x npix, coeffs: R x K (device), base: npix or NULL, out: R x npix. K <= 64 per
+ * call; accumulate != 0 adds to what `out` already holds (to chain more than 64 terms). */
+int lfd_opd_synth(const double *basis_dev, const double *coeffs_dev, const double *base_dev, int64_t npix,
+                  int32_t K, int32_t R, int32_t accumulate, double *out_dev, void *stream);
+
 /* ---- host-buffer convenience layer (what bench.py's e2e leg and the numpy shim call) ------
  * A context owns a device workspace, pinned staging buffers and one stream on `device`.
  */

@@ -50,6 +50,29 @@ abs_c128_kernel(const double2 *__restrict__ F, long long ld, int h, int w, doubl
     }
 }
 
+// OPD synthesis for Monte-Carlo wavefront error:
+//   out[r][pix] = base[pix] + sum_k coeffs[r][k] * basis[k][pix]
+// the np.einsum('ijk,i->jk', basis, coeff) of docs/user/wavefront_error.rst:118-135 for a batch of
+// coefficient vectors.  One thread per pixel keeps its K basis values in registers and streams
+// the R realisations: basis read once, 8 B/pixel/realisation written.
+constexpr int SYN_MAX_K = 64;
+__global__ void __launch_bounds__(256)
+opd_synth_kernel(const double *__restrict__ basis, const double *__restrict__ coeffs, const double *__restrict__ base,
+                 long long npix, int K, int R, int accumulate, double *__restrict__ out) {
+    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
+         pix += (long long)gridDim.x * blockDim.x) {
+        double b[SYN_MAX_K];
+#pragma unroll 8
+        for (int k = 0; k < K; ++k) b[k] = basis[(long long)k * npix + pix];
+        const double b0 = base ? base[pix] : 0.0;
+        for (int r = 0; r < R; ++r) {
+            double v = accumulate ? out[(long long)r * npix + pix] : b0;
+            for (int k = 0; k < K; ++k) v = fma(coeffs[(long long)r * K + k], b[k], v);
+            out[(long long)r * npix + pix] = v;
+        }
+    }
+}
+
 static inline unsigned grid_for(long long n) {
     long long b = (n + 255) / 256;
     return (unsigned)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
@@ -79,6 +102,16 @@ extern "C" int lfd_scale_separable(void *F, int64_t ld, int32_t h, int32_t w, co
 extern "C" int lfd_abs_c128(const void *F, int64_t ld, int32_t h, int32_t w, double *out, void *stream) {
     LFD_REQUIRE(F && out && h > 0 && w > 0 && ld >= w, "lfd_abs_c128: bad arguments");
     abs_c128_kernel<<<grid_for((long long)h * w), 256, 0, (cudaStream_t)stream>>>((const double2 *)F, ld, h, w, out);
+    LFD_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+extern "C" int lfd_opd_synth(const double *basis, const double *coeffs, const double *base, int64_t npix, int32_t K,
+                             int32_t R, int32_t accumulate, double *out, void *stream) {
+    LFD_REQUIRE(basis && coeffs && out && npix > 0 && K > 0 && R > 0, "lfd_opd_synth: bad arguments");
+    LFD_REQUIRE(K <= SYN_MAX_K, "lfd_opd_synth: at most %d basis terms per call (got %d)", SYN_MAX_K, K);
+    opd_synth_kernel<<<grid_for(npix), 256, 0, (cudaStream_t)stream>>>(basis, coeffs, base, npix, K, R, accumulate, out);
     LFD_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;

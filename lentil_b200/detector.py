@@ -58,3 +58,29 @@ def pixel(img, oversample=1):
     out = device.zeros_f64(h, w)
     _lib.check(L.lfd_abs_c128(g.data_ptr(), device.ld_of(g), h, w, out.data_ptr(), device.stream_ptr()), "lfd_abs_c128")
     return out if on_dev else device.to_host(out)
+
+
+def synthesize_opd(basis, coeffs, base=None, return_device=True):
+    """OPD maps from a modal basis: ``out[r] = base + sum_k coeffs[r, k] * basis[k]`` — the
+    ``np.einsum('ijk,i->jk', basis, coeff)`` of lentil's wavefront-error guide
+    (docs/user/wavefront_error.rst:118-135) for R coefficient vectors at once, on the device, so a
+    Monte-Carlo run never uploads R full OPD maps.  basis: (K, n, n); coeffs: (R, K) or (K,).
+    The result (R, n, n) can be passed as ``opds=`` to ``propagate_dft_batch``."""
+    b, _ = _to_dev(basis)
+    c = np.atleast_2d(np.asarray(coeffs, dtype=np.float64))
+    K, n0, n1 = (int(v) for v in b.shape)
+    if c.shape[1] != K:
+        raise ValueError(f'coeffs must have {K} columns')
+    R = c.shape[0]
+    cd = device.to_dev(c)
+    base_d = None if base is None else _to_dev(base)[0]
+    out = device.zeros_f64(R, n0, n1)
+    L = _lib.lib()
+    for k0 in range(0, K, 64):            # lfd_opd_synth takes at most 64 basis terms per call
+        kk = min(64, K - k0)
+        _lib.check(L.lfd_opd_synth(b[k0:k0 + kk].data_ptr(), cd[:, k0:k0 + kk].contiguous().data_ptr(),
+                                   base_d.data_ptr() if (base_d is not None and k0 == 0) else None,
+                                   n0 * n1, kk, R, 1 if k0 else 0, out.data_ptr(), device.stream_ptr()), "lfd_opd_synth")
+    if np.ndim(coeffs) == 1:
+        out = out[0]
+    return out if return_device else device.to_host(out)

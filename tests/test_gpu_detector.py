@@ -37,3 +37,36 @@ def test_pixel_preserves_radiometry_and_psf_chain():
     tot = float(psf.sum())
     assert abs(float(mtf.sum()) - tot) <= 1e-12 * tot and abs(float(det.sum()) - tot) <= 1e-12 * tot
     assert tuple(det.shape) == (64, 64)
+
+
+def test_opd_synthesis_matches_einsum_and_feeds_the_batch():
+    # docs/user/wavefront_error.rst:118-135: z = np.einsum('ijk,i->jk', basis, coeff)
+    from lentil_b200 import synth
+    import lentil_oracle as oc
+    rng = np.random.default_rng(31)
+    mask = synth.circle((96, 96), 45)
+    rows, cols = np.nonzero(mask)
+    rr, cc = np.meshgrid(np.arange(96) - 47.5, np.arange(96) - 47.5, indexing='ij')
+    rho, theta = np.hypot(rr, cc) / 46.0, np.arctan2(rr, cc)
+    basis = np.stack([synth.zernike(j, rho, theta) * mask for j in range(4, 37)])       # 33 modes
+    coeffs = rng.normal(size=(6, 33)) * 20e-9
+    base = rng.normal(size=(96, 96)) * 1e-9 * mask
+    got = lentil.detector.synthesize_opd(basis, coeffs, base=base, return_device=False)
+    ref = np.einsum('ijk,ri->rjk', basis, coeffs) + base
+    assert got.shape == (6, 96, 96)
+    assert peak_err(got, ref) <= 1e-14
+    one = lentil.detector.synthesize_opd(basis, coeffs[2], return_device=False)
+    assert peak_err(one, np.einsum('ijk,i->jk', basis, coeffs[2])) <= 1e-14
+    # more than 64 terms are chained
+    big_basis = rng.normal(size=(70, 16, 16))
+    big_c = rng.normal(size=(3, 70))
+    assert peak_err(lentil.detector.synthesize_opd(big_basis, big_c, return_device=False),
+                    np.einsum('ijk,ri->rjk', big_basis, big_c)) <= 1e-13
+    # device-resident OPD stack straight into the Monte-Carlo batch
+    opds = lentil.detector.synthesize_opd(basis, coeffs)
+    p = lentil.Pupil(amplitude=synth.normalize_power(mask), opd=np.zeros((96, 96)), pixelscale=1 / 90, focal_length=20.0)
+    wls, wts = np.array([6e-7, 7e-7]), np.array([0.5, 0.5])
+    stack = lentil.propagate_dft_batch(p, wls, 5e-6, (48, 48), oversample=2, weights=wts, opds=opds)
+    ref = oc.psf(p.amplitude, np.einsum('ijk,i->jk', basis, coeffs[4]), None, wls, wts, (1 / 90, 1 / 90), 20.0, 5e-6,
+                 (48, 48), None, 2)
+    assert peak_err(stack[4], ref) <= 1e-10
