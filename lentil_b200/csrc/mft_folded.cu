@@ -30,7 +30,13 @@
 // and stores them transposed.  The intermediate T never exists in HBM.
 //
 // Kernel structure otherwise follows mft_c128.cu: cos/sin A-fragments live in registers and
-// advance by a per-row rotation each DMMA k-step; ge/go tiles are staged with cp.async.
+// advance by a per-row rotation each DMMA k-step.
+//
+// Operand layout in HBM ("blocked"): ge/go are not stored as matrices but pre-tiled for the consumer,
+//     [column tile][K tile][plane ge|go][16 K rows][32 columns]   (16 KB per (column tile, K tile))
+// with the column index XOR-ed by 2*(row & 3), so that ONE cp.async.bulk per K tile lands a block in
+// shared memory exactly as the DMMA B-fragment loads want it (LDS.128, conflict-free, no padding).
+// Writers (fold_kernel, the row stage's epilogue) pay the permutation; the MMA warps issue no copies.
 #include "lfd_common.cuh"
 
 namespace lfd {
@@ -39,20 +45,26 @@ constexpr int FBR = 64;      // folded output rows per CTA
 constexpr int FBC = 32;      // complex data columns per CTA
 constexpr int FBK = 16;      // folded K rows per smem stage
 constexpr int FSTAGES = 4;
-constexpr int FLDS = FBC + 2;  // complex elements per smem row: LDS.128 conflict-free (see mft_c128.cu)
 constexpr int FTHREADS = 128;  // 4 warps stacked along the rows, each 16 folded rows x 32 complex columns
                                // (a twiddle element feeds 8 DMMAs); two CTAs per SM so that one CTA's
                                // prologue / epilogue hides under the other's MMAs
 constexpr int FRESEED_TILES = 64;  // re-seed the twiddle recurrence every 1024 folded K (2048 input rows)
 constexpr int FOLD_MAX_TILES = 1024;  // folded-column tiles per plane the support map can hold (inputs up to 32768 columns)
 constexpr int FIRST_WAVE_SMS = 148;  // B200: CTAs with linear id < 2*148 form the first wave
-constexpr size_t FSMEM_BYTES = (size_t)FSTAGES * 2 * FBK * FLDS * sizeof(double2);
+constexpr int FBLOCK_ELEMS = 2 * FBK * FBC;                      // complex elements per (column tile, K tile) block
+constexpr unsigned FBLOCK_BYTES = FBLOCK_ELEMS * sizeof(double2);   // 16 KB
+constexpr size_t FSMEM_BYTES = (size_t)FSTAGES * FBLOCK_BYTES;
+
+// element (K row r, plane p, slot sl) of column tile tl in a blocked operand with Kt K tiles
+__host__ __device__ __forceinline__ size_t blk_index(int Kt, int tl, int r, int p, int sl) {
+    return ((((size_t)tl * Kt + (r >> 4)) * 2 + p) * FBK + (r & 15)) * FBC + (sl ^ ((r & 3) << 1));
+}
 
 struct FoldDesc {
     const double2 *D;   // K x C
     long long ldd;
-    double2 *G;         // ge plane (Kf x C, ld = C) followed by go plane
-    int K, C, Kf, hm, cR2, pad_;
+    double2 *G;         // blocked ge/go operand of the row stage (see blk_index)
+    int K, C, Kf, hm, cR2, Kt;   // Kt = K tiles (rows padded to 16 are written as zeros)
     double alpha, sprime, sgn;
     // support map for the row stage: kmax[t] = 1 + last folded row with data in folded-column tile t,
     // kmax[ntile + t] = Kf - first such row (both start at 0 = empty; columns c and their mirrors share a
@@ -80,13 +92,13 @@ __device__ __forceinline__ double2 pupil_phasor(const FoldDesc &d, int i, int c)
 }
 
 struct FStageDesc {
-    const double2 *G;   // ge at G, go at G + Kf*C   (Kf x C each, ld = C)
-    double2 *O;         // FOLD_OUT: ge/go planes of the next stage (nKf x nldg each); else out (ld = ldo)
+    const double2 *G;   // blocked ge/go operand (blk_index, Ktiles K tiles)
+    double2 *O;         // FOLD_OUT: blocked operand of the next stage (nKtiles K tiles); else out (ld = ldo)
     long long ldo;
+    int Ktiles, nKtiles;
     int Kf, C, Rf, M, hM, cR2, cU2;
     int tiles_r, tiles_c;
     int nKf, nhm, ncR2;           // FOLD_OUT: folding of the data columns for the next stage
-    long long nldg;
     double alpha, oprime, sprime, scale, sgn;
     double nalpha, nsprime;
     // per-(plane, stage) phase tables built by phase_table_kernel, so that no CTA spends FP64
@@ -147,12 +159,17 @@ __device__ __forceinline__ void cmul(double xr, double xi, double yr, double yi,
     zi = xr * yi + xi * yr;
 }
 
-// ---- fold: g = pre * f, ge/go = g[+R'] +- g[-R'] -------------------------------------------------
+// ---- fold: g = pre * f, ge/go = g[+R'] +- g[-R'], written in the row stage's blocked layout --------
+// One CTA per folded K row (zero rows up to the next multiple of 16 included), one thread per slot:
+// slot sl of column tile tl is data column j+ = nhm + r2 (sl < 16) or its mirror j- = nhm - r2 - ncR2
+// (sl >= 16) for the folded column index r2 = 16 tl + (sl & 15), so that a lane of the row stage ends
+// up holding T[., j+] and T[., j-] side by side.
 __global__ void __launch_bounds__(256)
 fold_kernel(const FoldDesc *__restrict__ descs) {
     const FoldDesc d = descs[blockIdx.y];
     const int r = blockIdx.x;
-    if (r >= d.Kf) return;
+    if (r >= d.Kt * FBK) return;
+    const bool live = r < d.Kf;
     const double Rp = (double)r + 0.5 * d.cR2;
     __shared__ double pre[2];
     if (threadIdx.x == 0) {
@@ -161,81 +178,62 @@ fold_kernel(const FoldDesc *__restrict__ descs) {
         pre[0] = c;
         pre[1] = s;
     }
+    __shared__ int tile_nz[FOLD_MAX_TILES];
+    for (int t = threadIdx.x; t < d.ntile; t += blockDim.x) tile_nz[t] = 0;
     __syncthreads();
     const double pc = pre[0], ps = pre[1];
     const bool center = (d.cR2 == 0) && (r == 0);
     const int ip = d.hm + r, im = d.hm - r - d.cR2;
     const double2 *__restrict__ rowp = d.D + (long long)ip * d.ldd;
     const double2 *__restrict__ rowm = d.D + (long long)im * d.ldd;
-    double2 *__restrict__ ge = d.G + (long long)r * d.C;
-    double2 *__restrict__ go = d.G + ((long long)d.Kf + r) * d.C;
     const bool has_p = ip < d.K;
-    __shared__ int tile_nz[FOLD_MAX_TILES];
-    for (int t = threadIdx.x; t < d.ntile; t += blockDim.x) tile_nz[t] = 0;
-    __syncthreads();
-    for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
-        double2 a, b;
-        if (d.amp != nullptr) {
-            a = has_p ? pupil_phasor(d, ip, c) : make_double2(0.0, 0.0);
-            b = center ? make_double2(0.0, 0.0) : pupil_phasor(d, im, c);
-        } else {
-            a = has_p ? rowp[c] : make_double2(0.0, 0.0);
-            b = center ? make_double2(0.0, 0.0) : rowm[c];
+    const int nKf2 = (d.C + 1) / 2;
+    for (int s = threadIdx.x; s < d.ntile * FBC; s += blockDim.x) {
+        const int tl = s / FBC, sl = s % FBC;
+        const int r2 = tl * (FBC / 2) + (sl & 15);
+        const int j = (sl < 16) ? (d.nhm + r2) : (d.nhm - r2 - d.ncR2);
+        const bool ok = live && r2 < nKf2 && j >= 0 && j < d.C && !(sl >= 16 && d.ncR2 == 0 && r2 == 0);
+        double2 ge = make_double2(0.0, 0.0), go = ge;
+        if (ok) {
+            double2 a, b;
+            if (d.amp != nullptr) {
+                a = has_p ? pupil_phasor(d, ip, j) : make_double2(0.0, 0.0);
+                b = center ? make_double2(0.0, 0.0) : pupil_phasor(d, im, j);
+            } else {
+                a = has_p ? rowp[j] : make_double2(0.0, 0.0);
+                b = center ? make_double2(0.0, 0.0) : rowm[j];
+            }
+            const double2 gp = make_double2(a.x * pc - a.y * ps, a.x * ps + a.y * pc);
+            if (center) {
+                ge = gp;
+            } else {
+                const double2 gm = make_double2(b.x * pc + b.y * ps, b.y * pc - b.x * ps);   // conj(pre) * b
+                ge = make_double2(gp.x + gm.x, gp.y + gm.y);
+                go = make_double2(gp.x - gm.x, gp.y - gm.y);
+            }
+            if (a.x != 0.0 || a.y != 0.0 || b.x != 0.0 || b.y != 0.0) tile_nz[tl] = 1;   // benign race
         }
-        double2 gp = make_double2(a.x * pc - a.y * ps, a.x * ps + a.y * pc);
-        if (center) {
-            ge[c] = gp;
-            go[c] = make_double2(0.0, 0.0);
-        } else {
-            double2 gm = make_double2(b.x * pc + b.y * ps, b.y * pc - b.x * ps);   // conj(pre) * b
-            ge[c] = make_double2(gp.x + gm.x, gp.y + gm.y);
-            go[c] = make_double2(gp.x - gm.x, gp.y - gm.y);
-        }
-        if (a.x != 0.0 || a.y != 0.0 || b.x != 0.0 || b.y != 0.0) {
-            const int r2 = (c >= d.nhm) ? (c - d.nhm) : (d.nhm - c - d.ncR2);
-            tile_nz[r2 / (FBC / 2)] = 1;                       // benign race: everybody writes 1
-        }
+        d.G[blk_index(d.Kt, tl, r, 0, sl)] = ge;
+        d.G[blk_index(d.Kt, tl, r, 1, sl)] = go;
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < d.ntile; t += blockDim.x)
-        if (tile_nz[t]) {
-            atomicMax(d.kmax + t, r + 1);                        // 1 + last row with data
-            atomicMax(d.kmax + d.ntile + t, d.Kf - r);          // Kf - first row with data
-        }
+    if (live)
+        for (int t = threadIdx.x; t < d.ntile; t += blockDim.x)
+            if (tile_nz[t]) {
+                atomicMax(d.kmax + t, r + 1);                        // 1 + last row with data
+                atomicMax(d.kmax + d.ntile + t, d.Kf - r);          // Kf - first row with data
+            }
 }
 
 // ---- folded MFT stage ---------------------------------------------------------------------------
-// FOLD_OUT: smem columns 0..15 hold data columns j+ = nhm + r2, columns 16..31 their mirrors
-// j- = nhm - r2 - ncR2, for the 16 folded column indices r2 = cf_base .. cf_base+15.
-template <bool FOLD_OUT>
-__device__ __forceinline__ void f_load_tile(double2 *sd, const FStageDesc &d, int k_base, int c_base,
-                                            int tid) {
-#pragma unroll
-    for (int i = 0; i < 2 * FBK * FBC / FTHREADS; ++i) {
-        int idx = tid + i * FTHREADS;
-        int p = idx / (FBK * FBC), rem = idx % (FBK * FBC);
-        int kk = rem / FBC, cc = rem % FBC;
-        int gk = k_base + kk, gc;
-        bool ok = gk < d.Kf;
-        if (FOLD_OUT) {
-            int r2 = c_base + (cc & 15);
-            gc = (cc < 16) ? (d.nhm + r2) : (d.nhm - r2 - d.ncR2);
-            ok = ok && (r2 < d.nKf) && (gc >= 0) && (gc < d.C);
-        } else {
-            gc = c_base + cc;
-            ok = ok && (gc < d.C);
-        }
-        const double2 *src = ok ? (d.G + ((long long)p * d.Kf + gk) * d.C + gc) : d.G;
-        cp_async16(sd + (p * FBK + kk) * FLDS + cc, src, ok);
-    }
-}
-
+// FOLD_OUT (row stage): slots 0..15 of a column tile hold data columns j+ = nhm + r2, slots 16..31
+// their mirrors j- = nhm - r2 - ncR2, for the 16 folded column indices r2 = cf_base .. cf_base+15.
 template <bool FOLD_OUT>
 __global__ void __launch_bounds__(FTHREADS, 2)
 mft_folded_kernel(const FStageDesc *__restrict__ descs) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double2 *sD = reinterpret_cast<double2 *>(smem_raw);
-    constexpr int STAGE_ELEMS = 2 * FBK * FLDS;
+    __shared__ __align__(8) uint64_t bar_full[FSTAGES], bar_empty[FSTAGES];
 
 #ifdef LFD_TILE_TIMING
     long long tt[4];
@@ -277,11 +275,27 @@ mft_folded_kernel(const FStageDesc *__restrict__ descs) {
     }
     const int KT = (Kneed + FBK - 1) / FBK;
     const int KT0 = min(Kfirst / FBK, KT);
+    const int nkt = KT - KT0;
 
+    // operand pipeline: thread 0 issues one 16 KB bulk copy per K tile into a 4-slot ring; "full"
+    // barriers carry the byte count, "empty" barriers collect one arrival per warp
+    if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < FSTAGES - 1; ++s) {
-        if (KT0 + s < KT) f_load_tile<FOLD_OUT>(sD + s * STAGE_ELEMS, d, (KT0 + s) * FBK, c_base, tid);
-        cp_async_commit();
+        for (int s = 0; s < FSTAGES; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], FTHREADS / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const double2 *gblk = d.G + ((size_t)tc * d.Ktiles + KT0) * FBLOCK_ELEMS;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < FSTAGES - 1; ++s)
+            if (s < nkt) {
+                mbar_expect_tx(&bar_full[s], FBLOCK_BYTES);
+                bulk_g2s(sD + s * FBLOCK_ELEMS, gblk + (size_t)s * FBLOCK_ELEMS, FBLOCK_BYTES, &bar_full[s]);
+            }
     }
 
     // accA[mb][q][part]: A = cos-GEMM on ge; accB: B = sin-GEMM on go.  part 0 = Re columns, 1 = Im.
@@ -309,15 +323,21 @@ mft_folded_kernel(const FStageDesc *__restrict__ descs) {
         rs_[mb] = v.y;
     }
 
+    const int gx = g ^ (t << 1);                                         // swizzled column of this lane's B slot
     for (int kt = KT0; kt < KT; ++kt) {
-        cp_async_wait<FSTAGES - 2>();
-        __syncthreads();
-        if (kt == KT0) { LFD_TT(1) }
-        {
-            int nk = kt + FSTAGES - 1;
-            if (nk < KT) f_load_tile<FOLD_OUT>(sD + ((nk - KT0) % FSTAGES) * STAGE_ELEMS, d, nk * FBK, c_base, tid);
-            cp_async_commit();
+        const int j = kt - KT0, slot = j % FSTAGES;
+        if (tid == 0) {
+            const int nj = j + FSTAGES - 1;                              // refill the slot iteration j-1 used
+            if (nj < nkt) {
+                const int ns = nj % FSTAGES;
+                if (nj >= FSTAGES) mbar_wait(&bar_empty[ns], ((nj / FSTAGES) - 1) & 1);
+                mbar_expect_tx(&bar_full[ns], FBLOCK_BYTES);
+                bulk_g2s(sD + ns * FBLOCK_ELEMS, gblk + (size_t)nj * FBLOCK_ELEMS, FBLOCK_BYTES, &bar_full[ns]);
+            }
         }
+        __syncwarp();
+        mbar_wait(&bar_full[slot], (j / FSTAGES) & 1);
+        if (kt == KT0) { LFD_TT(1) }
         if (kt == 0) {
 #pragma unroll
             for (int mb = 0; mb < 2; ++mb) {
@@ -332,16 +352,16 @@ mft_folded_kernel(const FStageDesc *__restrict__ descs) {
             cis_cycles(d.alpha, rp, 8.0, 1.0, sc, ss);
             cmul(tc_[0], ts_[0], sc, ss, tc_[1], ts_[1]);
         }
-        const double2 *se = sD + ((kt - KT0) % FSTAGES) * STAGE_ELEMS + g;
-        const double2 *so = se + FBK * FLDS;
+        const double2 *se = sD + slot * FBLOCK_ELEMS + t * FBC + gx;
+        const double2 *so = se + FBK * FBC;
 
 #pragma unroll
         for (int ks = 0; ks < FBK / 4; ++ks) {
             double2 ve[4], vo[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                ve[q] = se[(ks * 4 + t) * FLDS + q * 8];
-                vo[q] = so[(ks * 4 + t) * FLDS + q * 8];
+                ve[q] = se[ks * 4 * FBC + q * 8];
+                vo[q] = so[ks * 4 * FBC + q * 8];
             }
             // next k-step's twiddles, issued ahead of this step's MMAs (separate registers)
             double ntc[2], nts[2];
@@ -367,8 +387,9 @@ mft_folded_kernel(const FStageDesc *__restrict__ descs) {
                 ts_[mb] = nts[mb];
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[slot]);
     }
-    cp_async_wait<0>();
     LFD_TT(2)
 
     // ---- epilogue: unfold to the +U' and -U' output rows, post phase, scale, transposed store ----
@@ -428,7 +449,7 @@ mft_folded_kernel(const FStageDesc *__restrict__ descs) {
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const int r2 = c_base + qq * 8 + 2 * t + i;
-                    if (r2 >= d.nKf) continue;
+                    const bool pad_row = r2 >= d.nKf;                     // zero K rows of the column stage
                     const bool center = (d.ncR2 == 0) && (r2 == 0);
                     // column j+ lives in q = qq, its mirror j- in q = qq + 2
                     const double Apr = accA[mb][qq][0][i], Api = accA[mb][qq][1][i];
@@ -436,8 +457,6 @@ mft_folded_kernel(const FStageDesc *__restrict__ descs) {
                     const double Amr = accA[mb][qq + 2][0][i], Ami = accA[mb][qq + 2][1][i];
                     const double Bmr = d.sgn * accB[mb][qq + 2][0][i], Bmi = d.sgn * accB[mb][qq + 2][1][i];
                     const double pc2 = p2c[qq][i], ps2 = p2s[qq][i];
-                    double2 *ge = d.O + (long long)r2 * d.nldg;
-                    double2 *go = d.O + ((long long)d.nKf + r2) * d.nldg;
 #pragma unroll
                     for (int side = 0; side < 2; ++side) {
                         if (side == 0 ? !has_p : !has_m) continue;
@@ -451,12 +470,18 @@ mft_folded_kernel(const FStageDesc *__restrict__ descs) {
                         cmul(xr, xi, pc, ps, tmr, tmi);                   // T[k][j-]
                         cmul(tpr, tpi, pc2, ps2, gpr, gpi);               // pre2 * T+
                         cmul(tmr, tmi, pc2, -ps2, gmr, gmi);              // conj(pre2) * T-
-                        if (center) {
-                            ge[k] = make_double2(gpr, gpi);
-                            go[k] = make_double2(0.0, 0.0);
+                        // column k of the column stage: tile k / 32, slot k % 32
+                        double2 *ge = d.O + blk_index(d.nKtiles, k / FBC, r2, 0, k % FBC);
+                        double2 *go = ge + FBK * FBC;
+                        if (pad_row) {
+                            *ge = make_double2(0.0, 0.0);
+                            *go = make_double2(0.0, 0.0);
+                        } else if (center) {
+                            *ge = make_double2(gpr, gpi);
+                            *go = make_double2(0.0, 0.0);
                         } else {
-                            ge[k] = make_double2(gpr + gmr, gpi + gmi);
-                            go[k] = make_double2(gpr - gmr, gpi - gmi);
+                            *ge = make_double2(gpr + gmr, gpi + gmi);
+                            *go = make_double2(gpr - gmr, gpi - gmi);
                         }
                     }
                 }
@@ -476,14 +501,22 @@ static inline size_t f_align(size_t v, size_t a) { return (v + a - 1) / a * a; }
 constexpr long long SKEW_CYCLES_PER_KTILE = 2400;   // half of the ~4.7k cycles two co-resident CTAs spend per k-tile
 constexpr size_t SLOT_BYTES = 2 * 256 * sizeof(unsigned);   // per-SM slot counters, one set per MFT launch
 
+// blocked operand sizes: row stage = ceil(Kf2/16) column tiles x ceil(Kf1/16) K tiles, column stage =
+// ceil(M/32) column tiles x ceil(Kf2/16) K tiles, 16 KB each
+static inline size_t g1_bytes(const lfd_mft_desc &p) {
+    return (size_t)(((p.n + 1) / 2 + FBC / 2 - 1) / (FBC / 2)) * (((p.m + 1) / 2 + FBK - 1) / FBK) * FBLOCK_BYTES;
+}
+static inline size_t g2_bytes(const lfd_mft_desc &p) {
+    return (size_t)((p.M + FBC - 1) / FBC) * (((p.n + 1) / 2 + FBK - 1) / FBK) * FBLOCK_BYTES;
+}
+
 size_t folded_workspace_bytes(const lfd_mft_desc *descs, int count) {
     size_t kmax_ints = 0;
     for (int i = 0; i < count; ++i) kmax_ints += 2 * (((descs[i].n + 1) / 2 + FBC / 2 - 1) / (FBC / 2));
     size_t bytes = f_align((size_t)count * (sizeof(FoldDesc) + 2 * sizeof(FStageDesc)) + SLOT_BYTES + kmax_ints * sizeof(int), 256);
     for (int i = 0; i < count; ++i) {
         const lfd_mft_desc &p = descs[i];
-        bytes += f_align((size_t)2 * ((p.m + 1) / 2) * p.n * sizeof(double2), 256);
-        bytes += f_align((size_t)2 * ((p.n + 1) / 2) * p.M * sizeof(double2), 256);
+        bytes += g1_bytes(p) + g2_bytes(p);
         const int Rfp1 = ((p.M + 1) / 2 + FBR - 1) / FBR * FBR, Rfp2 = ((p.N + 1) / 2 + FBR - 1) / FBR * FBR;
         const int nKfp = ((p.n + 1) / 2 + FBC / 2 - 1) / (FBC / 2) * (FBC / 2);
         bytes += f_align((table_elems(Rfp1, nKfp) + table_elems(Rfp2, 0)) * sizeof(double2), 256);
@@ -528,10 +561,11 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
             LFD_REQUIRE(false, "lfd_mft_c128_batched: plane %d has invalid shape/ld/pointers", i);
         }
         const int Kf1 = (p.m + 1) / 2, Kf2 = (p.n + 1) / 2;
+        const int Kt1 = (Kf1 + FBK - 1) / FBK, Kt2 = (Kf2 + FBK - 1) / FBK;
         double2 *G1 = (double2 *)(ws + off);
-        off += f_align((size_t)2 * Kf1 * p.n * sizeof(double2), 256);
+        off += g1_bytes(p);
         double2 *G2 = (double2 *)(ws + off);
-        off += f_align((size_t)2 * Kf2 * p.M * sizeof(double2), 256);
+        off += g2_bytes(p);
         const int Rfp1 = ((p.M + 1) / 2 + FBR - 1) / FBR * FBR, Rfp2 = ((p.N + 1) / 2 + FBR - 1) / FBR * FBR;
         const int nKfp = (Kf2 + FBC / 2 - 1) / (FBC / 2) * (FBC / 2);
         double2 *tab1 = (double2 *)(ws + off);
@@ -546,7 +580,7 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
 
         FoldDesc &fd = hf[i];
         fd.D = (const double2 *)p.f; fd.ldd = p.ldf; fd.G = G1;
-        fd.K = p.m; fd.C = p.n; fd.Kf = Kf1; fd.hm = p.m / 2; fd.cR2 = cRm; fd.pad_ = 0;
+        fd.K = p.m; fd.C = p.n; fd.Kf = Kf1; fd.hm = p.m / 2; fd.cR2 = cRm; fd.Kt = Kt1;
         fd.alpha = p.alpha_r; fd.sprime = p.shift_r + 0.5 * cUM; fd.sgn = sgn;
         if (src) {
             fd.D = nullptr; fd.ldd = 0;
@@ -558,7 +592,7 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
         fd.nhm = p.n / 2; fd.ncR2 = cRn; fd.ntile = (Kf2 + FBC / 2 - 1) / (FBC / 2); fd.pad2_ = 0;
         fd.kmax = kmax_dev;
         if (fd.ntile > FOLD_MAX_TILES) { free(h); LFD_REQUIRE(false, "lfd_mft_c128_batched: plane %d is too wide (%d columns)", i, p.n); }
-        if (Kf1 > max_rows) max_rows = Kf1;
+        if (Kt1 * FBK > max_rows) max_rows = Kt1 * FBK;
 
         // stage 1 (rows): K = m, C = n, output rows M; result folded along its columns for stage 2
         FStageDesc &s1 = hs[i];
@@ -567,7 +601,7 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
         s1.cR2 = cRm; s1.cU2 = cUM;
         s1.alpha = p.alpha_r; s1.oprime = p.off_r - 0.5 * cRm; s1.sprime = p.shift_r + 0.5 * cUM;
         s1.scale = 1.0; s1.sgn = sgn;
-        s1.nKf = Kf2; s1.nhm = p.n / 2; s1.ncR2 = cRn; s1.nldg = p.M;
+        s1.nKf = Kf2; s1.nhm = p.n / 2; s1.ncR2 = cRn; s1.Ktiles = Kt1; s1.nKtiles = Kt2;
         s1.nalpha = p.alpha_c; s1.nsprime = p.shift_c + 0.5 * cUN;
         s1.tab = tab1; s1.Rfp = Rfp1; s1.nKfp = nKfp;
         s1.kmax = kmax_dev; s1.ntile = fd.ntile; kmax_dev += 2 * fd.ntile;
@@ -582,7 +616,7 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
         s2.cR2 = cRn; s2.cU2 = cUN;
         s2.alpha = p.alpha_c; s2.oprime = p.off_c - 0.5 * cRn; s2.sprime = p.shift_c + 0.5 * cUN;
         s2.scale = scale; s2.sgn = sgn;
-        s2.nKf = 0; s2.nhm = 0; s2.ncR2 = 0; s2.nldg = 0; s2.nalpha = 0.0; s2.nsprime = 0.0;
+        s2.nKf = 0; s2.nhm = 0; s2.ncR2 = 0; s2.Ktiles = Kt2; s2.nKtiles = 0; s2.nalpha = 0.0; s2.nsprime = 0.0;
         s2.tab = tab2; s2.Rfp = Rfp2; s2.nKfp = 0; s2.kmax = nullptr; s2.ntile = 0; s2.intensity = intensity_out; s1.intensity = 0;
         s2.sm_slots = slots_dev + 256; s2.skew_cycles = (long long)((Kf2 + FBK - 1) / FBK) * SKEW_CYCLES_PER_KTILE;
         s2.tiles_r = (s2.Rf + FBR - 1) / FBR; s2.tiles_c = (s2.C + FBC - 1) / FBC;
