@@ -15,7 +15,7 @@ __version__ = '0.1.0'
 from .ptype import ptype, none, pupil, image, tilt, transform  # noqa: F401
 from . import extent, helper, field, fourier, plane, propagate, wavefront, device, detector  # noqa: F401
 from .field import Field  # noqa: F401
-from .plane import Plane, Pupil, Image, Tilt  # noqa: F401
+from .plane import Plane, Pupil, Image, Tilt, DispersiveTilt, Grism  # noqa: F401
 from .wavefront import Wavefront  # noqa: F401
 from .propagate import propagate_dft, propagate_dft_batch  # noqa: F401
 from .helper import boundary  # noqa: F401

@@ -505,3 +505,94 @@ class Tilt(_TiltBase):
 
     def __shift__(self, xs=0, ys=0, z=0, **kwargs):
         return xs - (z * self.x), ys - (z * self.y)
+
+
+_GL_NODES, _GL_WEIGHTS = np.polynomial.legendre.leggauss(48)
+
+
+class DispersiveTilt(_TiltBase):
+    """Spectral dispersion acting as a wavelength-dependent tilt (lentil/plane.py:926-1096).
+
+    ``dispersion`` maps distance along the spectral trace to wavelength, ``trace`` maps focal-plane
+    x to y (both polynomial coefficients, highest power first, metres).  ``__shift__`` returns the
+    focal-plane position of `wavelength` along the trace, anchored at the undispersed source.
+
+    First-order polynomials are solved in closed form exactly as the reference does
+    (:1030-1033, :1043-1045).  Higher orders, which the reference hands to scipy's ``leastsq`` /
+    ``quad`` one scalar at a time (:1037, :1050), are solved here by a safeguarded Newton iteration
+    on the polynomial and on a Gauss-Legendre arc length — vectorised, so a whole wavelength grid
+    costs one call (the batch driver evaluates every plane's shift up front).
+    """
+
+    def __init__(self, trace=None, dispersion=None, **kwargs):
+        super().__init__(**kwargs)
+        if trace is not None:
+            self.trace = np.asarray(trace)
+        if dispersion is not None:
+            self.dispersion = np.asarray(dispersion)
+
+    def __shift__(self, wavelength, xs=0., ys=0., **kwargs):
+        x, y = self._pos(self._dist(wavelength))
+        return x + xs, y + ys
+
+    # ---- wavelength -> distance along the trace ---------------------------------------------------
+    def _dist(self, wavelength):
+        disp = np.asarray(self.dispersion, dtype=float)
+        if len(disp) == 2:
+            return (wavelength - disp[1]) / disp[0]
+        wavelength = np.asarray(wavelength, dtype=float)
+        dpoly = np.polyder(disp)
+        d = np.zeros_like(wavelength)
+        done = np.zeros(wavelength.shape, dtype=bool)
+        with np.errstate(all='ignore'):
+            for _ in range(100):
+                step = (np.polyval(disp, d) - wavelength) / np.polyval(dpoly, d)
+                d = np.where(done, d, d - step)
+                done |= np.abs(step) <= 1e-15 * np.maximum(np.abs(d), 1e-300)
+                if np.all(done):
+                    break
+        if not np.all(done):
+            # no real root for these wavelengths: the reference's least-squares solve settles on
+            # the stationary point of the residual, i.e. a root of the derivative (:1037)
+            ddpoly = np.polyder(dpoly)
+            e = np.zeros_like(wavelength)
+            for _ in range(100):
+                step = np.polyval(dpoly, e) / np.polyval(ddpoly, e)
+                e = e - step
+                if np.all(np.abs(step) <= 1e-15 * np.maximum(np.abs(e), 1e-300)):
+                    break
+            d = np.where(done, d, e)
+        return d
+
+    # ---- distance along the trace -> (x, y) -------------------------------------------------------
+    def _arc_len(self, x):
+        """Arc length of the trace from 0 to x (Gauss-Legendre on sqrt(1 + y'(t)^2))."""
+        slope = np.polyder(np.asarray(self.trace, dtype=float))
+        x = np.asarray(x, dtype=float)
+        t = 0.5 * x[..., None] * (_GL_NODES + 1.0)
+        return 0.5 * x * np.sum(_GL_WEIGHTS * np.sqrt(1.0 + np.polyval(slope, t) ** 2), axis=-1)
+
+    def _pos(self, dist):
+        trace = np.asarray(self.trace, dtype=float)
+        if len(trace) == 2:
+            x = dist / np.sqrt(1 + trace[0] ** 2)
+        else:
+            slope = np.polyder(trace)
+            dist = np.asarray(dist, dtype=float)
+            x = dist / np.sqrt(1.0 + np.polyval(slope, 0.0) ** 2)
+            for _ in range(100):
+                step = (self._arc_len(x) - dist) / np.sqrt(1.0 + np.polyval(slope, x) ** 2)
+                x = x - step
+                if np.all(np.abs(step) <= 1e-15 * np.maximum(np.abs(x), 1e-300)):
+                    break
+        return x, np.polyval(trace, x)
+
+
+class Grism(DispersiveTilt):
+    """Deprecated alias of :class:`DispersiveTilt` (lentil/plane.py:1099-1167 warns the same way)."""
+
+    def __init__(self, trace, dispersion, **kwargs):
+        import warnings
+        warnings.warn("Grism is deprecated; DispersiveTilt replaces it.", DeprecationWarning,
+                      stacklevel=2)
+        super().__init__(trace=trace, dispersion=dispersion, **kwargs)

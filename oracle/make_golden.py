@@ -295,6 +295,23 @@ def golden_detector():
     print("detector: oracle == reference bit-for-bit (rebin 2-D / cube, pixel MTF even / odd size)")
 
 
+def golden_dispersive_tilt():
+    # the reference solves higher-order trace/dispersion polynomials with scipy leastsq / quad to
+    # ~1e-8 relative (lentil/plane.py:1037,1050); these vectors pin the host mirror to that level
+    wl = np.linspace(500e-9, 900e-9, 9)
+    cases = [([2.0, 0.0], [1.0, 650e-9]),                    # both first order (closed form)
+             ([3.0, 0.2, 0.0], [5e-6, 650e-9]),              # second-order trace
+             ([0.5, 1e-3], [2e-4, 1e-5, 500e-9]),            # second-order dispersion
+             ([40.0, -3.0, 0.1, 0.0], [1e-3, 2e-5, 450e-9])]   # third-order trace, second-order dispersion
+    d = dict(wl=wl, n=np.array(len(cases)))
+    for i, (trace, disp) in enumerate(cases):
+        dt = lentil.DispersiveTilt(trace=trace, dispersion=disp)
+        xy = np.array([[float(np.ravel(v)[0]) for v in dt.__shift__(wavelength=w, xs=1e-3, ys=-2e-3)] for w in wl])
+        d[f"c{i}_trace"], d[f"c{i}_disp"], d[f"c{i}_xy"] = np.array(trace), np.array(disp), xy
+    np.savez_compressed(os.path.join(GOLD, "dispersive_tilt.npz"), **d)
+    print("dispersive tilt: reference shifts for", len(cases), "polynomial pairs x", len(wl), "wavelengths")
+
+
 if __name__ == "__main__":
     assert lentil.__version__ == "0.8.8", lentil.__version__
     golden_dft2()
@@ -302,5 +319,6 @@ if __name__ == "__main__":
     golden_field()
     golden_propagate()
     golden_detector()
+    golden_dispersive_tilt()
     sizes = {f: os.path.getsize(os.path.join(GOLD, f)) for f in sorted(os.listdir(GOLD))}
     print("fixtures:", sizes)

@@ -213,3 +213,52 @@ def test_freeze_semantics():
     p.thaw()
     p.opd = np.ones((4, 4))
     assert p.size == 1 and p.shape == (4, 4)
+
+
+# ---- DispersiveTilt (lentil/plane.py:926-1167) --------------------------------------------------------
+def test_dispersive_tilt_center_and_shift():
+    # reference tests/test_plane.py:163-181
+    dt = lentil.DispersiveTilt(dispersion=[1, 650e-9], trace=[2, 0])
+    x, y = dt.__shift__(wavelength=650e-9, xs=1.25, ys=-3.5)
+    assert x == 1.25 and y == -3.5
+    dt = lentil.DispersiveTilt(trace=[1, 1], dispersion=[1, 650e-9])
+    x, y = dt.__shift__(wavelength=900e-9)
+    assert x == (900e-9 - dt.dispersion[1]) / np.sqrt(2) and y == 1 + x
+
+
+def test_dispersive_tilt_class_attribute_overload():
+    # reference tests/test_plane.py:213-219
+    class Disperser(lentil.DispersiveTilt):
+        dispersion = [1, 0]
+        trace = [1, 0]
+    assert np.allclose(Disperser().__shift__(1), np.sqrt(2) / 2)
+    assert Disperser().ptype == lentil.tilt
+
+
+def test_dispersive_tilt_matches_reference_vectors(golden):
+    d = golden("dispersive_tilt")
+    wl = d["wl"]
+    for i in range(int(d["n"])):
+        dt = lentil.DispersiveTilt(trace=d[f"c{i}_trace"], dispersion=d[f"c{i}_disp"])
+        ref = d[f"c{i}_xy"]
+        x, y = dt.__shift__(wavelength=wl, xs=1e-3, ys=-2e-3)           # whole grid in one call
+        scale = np.max(np.abs(ref))
+        assert np.max(np.abs(x - ref[:, 0])) <= 2e-7 * scale and np.max(np.abs(y - ref[:, 1])) <= 2e-7 * scale
+        for k in (0, len(wl) - 1):                                       # scalar calls agree with the grid
+            xs, ys = dt.__shift__(wavelength=float(wl[k]), xs=1e-3, ys=-2e-3)
+            assert np.isclose(xs, x[k], rtol=1e-13, atol=0) and np.isclose(ys, y[k], rtol=1e-13, atol=0)
+
+
+def test_grism_alias_warns():
+    with pytest.warns(DeprecationWarning):
+        g = lentil.Grism(trace=[1, 0], dispersion=[1, 0])
+    assert np.allclose(g.__shift__(1), np.sqrt(2) / 2)
+
+
+def test_dispersive_tilt_in_propagation_shift_chain():
+    # a DispersiveTilt in a Field's tilt list moves the window by the dispersed position
+    dt = lentil.DispersiveTilt(trace=[0.5, 0.0], dispersion=[2e-3, 650e-9])
+    w = dt * lentil.Wavefront(700e-9)
+    x, y = dt.__shift__(wavelength=700e-9)
+    r, c = w.data[0].shift(z=10.0, wavelength=700e-9, pixelscale=(5e-6, 5e-6), oversample=2)
+    assert np.isclose(r, -y / 5e-6 * 2) and np.isclose(c, x / 5e-6 * 2)
