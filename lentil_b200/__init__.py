@@ -17,7 +17,7 @@ from . import extent, helper, field, fourier, plane, propagate, wavefront, devic
 from .field import Field  # noqa: F401
 from .plane import Plane, Pupil, Image, Tilt, DispersiveTilt, Grism  # noqa: F401
 from .wavefront import Wavefront  # noqa: F401
-from .propagate import propagate_dft, propagate_dft_batch  # noqa: F401
+from .propagate import propagate_dft, propagate_dft_batch, propagate_fft, scratch_shape  # noqa: F401
 from .helper import boundary  # noqa: F401
 from .device import set_device  # noqa: F401
 from .detector import rebin  # noqa: F401

@@ -127,6 +127,81 @@ def propagate_dft(wavefront, pixelscale, shape=None, prop_shape=None, oversample
     return out
 
 
+def _fft_shape(dx, du, z, wavelength, oversample):
+    """Padded size whose FFT bin spacing realises the requested sampling, and the wavelength the
+    integer padding really corresponds to (lentil/propagate.py:126-132)."""
+    alpha = _dft_alpha(dx, du, wavelength, z, oversample)
+    fft_shape = np.round(np.reciprocal(alpha)).astype(int)
+    prop_wavelength = np.min((fft_shape / oversample * dx * du) / z)
+    return fft_shape, prop_wavelength
+
+
+def scratch_shape(wavelength, dx, du, z, oversample):
+    """Scratch shape an FFT propagation of the longest wavelength needs (lentil/propagate.py:91-118)."""
+    dx, du = np.broadcast_to(dx, (2,)), np.broadcast_to(du, (2,))
+    fft_shape, _ = _fft_shape(dx, du, z, np.max(wavelength), oversample)
+    return tuple(fft_shape)
+
+
+def _padded_fft_geometry(have, npix):
+    """Rows (or columns) of a `have`-long dense field that survive lentil.util.pad to `npix`
+    (util.py:31-90: centred pad, centre crop when larger), and the dft2 offset/shift that make
+    the matrix transform of just those rows equal to ``ifftshift(fft(fftshift(padded)))``.
+
+    With h = npix // 2 the shifted FFT is  sum_j x[j] e^{-2 pi i (j+h)(k+h)/npix}; in centred
+    coordinates R = j - h, U = k - h that is e^{-2 pi i RU/npix} for even npix (2h = npix) and
+    e^{-2 pi i (R-1)(U-1)/npix} for odd npix (2h = npix - 1): offset -1, shift +1."""
+    if npix - have <= 0:
+        src0, keep, dst0 = (have - npix) // 2, npix, 0
+    else:
+        src0, keep, dst0 = 0, have, (npix - have) // 2
+    odd = npix % 2
+    offset = dst0 + keep // 2 - npix // 2 - odd
+    return src0, keep, offset, odd
+
+
+def propagate_fft(wavefront, pixelscale, shape=None, oversample=2, scratch=None):
+    """Far-field propagation on the FFT's sampling grid (lentil/propagate.py:9-88).
+
+    Same parameters, errors and result as the reference: the dense wavefront field is zero-padded
+    to ``round(1/alpha)`` samples, transformed with an orthonormal shifted FFT, and returned as ONE
+    Field of the padded size inside a Wavefront of ``shape * oversample`` whose wavelength is the
+    one the integer padding really samples.  NotImplementedError for fields that carry tilt,
+    ValueError when `shape` exceeds the padded size or `scratch` is too small.
+
+    On the device the padded array never exists: the transform of the non-zero rows and columns is
+    a K2a launch with alpha = 1/npix (the same sum the FFT evaluates, term for term), so `scratch`
+    is validated and otherwise unused."""
+    if any(f.tilt for f in wavefront.data):
+        raise NotImplementedError('propagate_fft does not support Wavefronts with fitted tilt. '
+                                  'Use propagate_dft instead.')
+    ptype_out = _propagate_ptype(wavefront.ptype, method='fraunhofer')
+    du = np.broadcast_to(pixelscale, (2,))
+    fft_shape, prop_wavelength = _fft_shape(wavefront.pixelscale, du, wavefront.focal_length,
+                                            wavefront.wavelength, oversample)
+    if shape is None:
+        shape_out = tuple(int(v) for v in fft_shape)
+    else:
+        shape = tuple(np.broadcast_to(shape, (2,)))
+        if np.any(shape > fft_shape / oversample):
+            raise ValueError(f'requested shape {tuple(shape)} is larger in at least one dimension than '
+                             f'maximum propagation shape {tuple(fft_shape // oversample)}')
+        shape_out = (shape[0] * oversample, shape[1] * oversample)
+    if scratch is not None and not all(np.asarray(scratch.shape) > fft_shape):
+        raise ValueError(f'scratch must have shape greater than or equal to {tuple(fft_shape)}')
+
+    out = Wavefront.empty(wavelength=prop_wavelength, pixelscale=du / oversample,
+                          focal_length=wavefront.focal_length, shape=shape_out, ptype=ptype_out)
+    dense = wavefront._accumulate(device.empty_c128(*wavefront.shape).zero_(), 1, False)   # K3
+    r0, nr, off_r, odd_r = _padded_fft_geometry(int(dense.shape[0]), int(fft_shape[0]))
+    c0, nc, off_c, odd_c = _padded_fft_geometry(int(dense.shape[1]), int(fft_shape[1]))
+    F = _fourier.dft2_dev(dense[r0:r0 + nr, c0:c0 + nc], alpha=(1.0 / fft_shape[0], 1.0 / fft_shape[1]),
+                          shape=(int(fft_shape[0]), int(fft_shape[1])), shift=(odd_r, odd_c),
+                          offset=(off_r, off_c), unitary=True)                             # K2a
+    out.data.append(Field(data=F, pixelscale=du / oversample))
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # batched driver
 # ----------------------------------------------------------------------------------------------

@@ -420,6 +420,58 @@ def psf(amplitude, opd, mask, wavelengths, weights, dx, z, pixelscale, shape, pr
 
 
 # --------------------------------------------------------------------------------------------
+# the FFT sibling of propagate_dft (next row): lentil/propagate.py:9-136, lentil/util.py:31-90
+# --------------------------------------------------------------------------------------------
+
+
+def pad(array, shape):
+    """Centred zero-pad (or centre crop where the array is larger), lentil/util.py:31-90, 2-D case."""
+    array = np.asarray(array)
+    src, dst = [], []
+    for have, want in zip(array.shape, shape):
+        if want - have <= 0:
+            lo = (have - want) // 2
+            src.append(slice(lo, lo + want))
+            dst.append(slice(0, want))
+        else:
+            lo = (want - have) // 2
+            src.append(slice(0, have))
+            dst.append(slice(lo, lo + have))
+    padded = np.zeros((shape[0], shape[1]), dtype=array.dtype)
+    padded[tuple(dst)] = array[tuple(src)]
+    return padded
+
+
+def fft_shape(dx, du, z, wavelength, oversample):
+    """Padded size that realises the requested sampling, and the wavelength that the integer
+    padding really corresponds to, lentil/propagate.py:126-132."""
+    alpha = dft_alpha(dx, du, z, wavelength, oversample)     # z / wavelength swapped as in :129 (a product)
+    npix = np.round(np.reciprocal(alpha)).astype(int)
+    prop_wavelength = np.min((npix / oversample * dx * du) / z)
+    return npix, prop_wavelength
+
+
+def propagate_fft(fields, wf_shape, wavelength, dx, z, pixelscale, shape=None, oversample=2):
+    """lentil/propagate.py:9-88 (no-scratch branch): dense field -> centred pad -> shifted
+    orthonormal FFT (:135-136).  Returns (output field, shape_out, propagation wavelength)."""
+    if any(f["tilt"] for f in fields):
+        raise NotImplementedError('propagate_fft does not support Wavefronts with fitted tilt.')
+    dx = np.broadcast_to(dx, (2,))
+    du = np.broadcast_to(pixelscale, (2,))
+    npix, prop_wavelength = fft_shape(dx, du, z, wavelength, oversample)
+    if shape is None:
+        shape_out = tuple(int(v) for v in npix)
+    else:
+        shape = tuple(np.broadcast_to(shape, (2,)))
+        if np.any(shape > npix / oversample):
+            raise ValueError('requested shape is larger than the maximum propagation shape')
+        shape_out = (int(shape[0] * oversample), int(shape[1] * oversample))
+    x = pad(wavefront_field(fields, wf_shape), npix)
+    F = np.fft.ifftshift(np.fft.fft2(np.fft.fftshift(x), norm='ortho'))
+    return make_field(F, (0, 0)), shape_out, prop_wavelength
+
+
+# --------------------------------------------------------------------------------------------
 # detector-side sampling (next rows): lentil/util.py:221-258, lentil/detector.py:167-220
 # --------------------------------------------------------------------------------------------
 

@@ -312,6 +312,41 @@ def golden_dispersive_tilt():
     print("dispersive tilt: reference shifts for", len(cases), "polynomial pairs x", len(wl), "wavelengths")
 
 
+def golden_propagate_fft():
+    """propagate_fft (lentil/propagate.py:9-88): even and odd padded sizes, default and explicit
+    shape, one segmented pupil; plus the scratch_shape helper and the two error cases."""
+    rng = np.random.default_rng(5)
+    d = {}
+    cases = [  # n, radius, dx, z, du, wl, shape, oversample
+        (40, 18, 1 / 36, 10.0, 5e-6, 650e-9, (24, 24), 2),     # alpha -> 94 samples (even)
+        (40, 18, 1 / 36, 10.0, 5e-6, 655e-9, None, 2),          # -> 94, default shape
+        (41, 19, 1 / 38, 8.0, 6e-6, 600e-9, (20, 30), 1),       # -> odd padded size (30.4 -> 30; 8*600e-9*38/6e-6)
+        (36, 16, 1 / 32, 10.0, 5e-6, 555e-9, (15, 15), 3),      # odd padded size 107
+    ]
+    for i, (n, radius, dx, z, du, wl, shape, os_) in enumerate(cases):
+        amp, opd, _ = make_pupil(n, radius, rng.normal(size=6) * 40e-9, rng)
+        p = lentil.Pupil(amplitude=amp, opd=opd, pixelscale=dx, focal_length=z)
+        w = lentil.Wavefront(wl) * p
+        w2 = lentil.propagate_fft(w, pixelscale=du, shape=shape, oversample=os_)
+        fo = oc.plane_multiply([oc.make_field(np.array(1, dtype=complex))], amp, opd, None, wl)
+        Fo, shape_out, pw = oc.propagate_fft(fo, w.shape, wl, (dx, dx), z, du, shape, os_)
+        assert np.array_equal(Fo["data"], w2.data[0].data) and tuple(shape_out) == tuple(w2.shape)
+        assert pw == w2.wavelength
+        assert np.array_equal(oc.wavefront_intensity([Fo], shape_out), w2.intensity)
+        d.update({f"c{i}_amp": amp, f"c{i}_opd": opd, f"c{i}_dx": np.array(dx), f"c{i}_z": np.array(z),
+                  f"c{i}_du": np.array(du), f"c{i}_wl": np.array(wl),
+                  f"c{i}_shape": np.array(shape if shape is not None else (-1, -1)), f"c{i}_os": np.array(os_),
+                  f"c{i}_shape_out": np.array(w2.shape),
+                  f"c{i}_prop_wl": np.array(w2.wavelength), f"c{i}_intensity": w2.intensity})
+        if i != 1:                                   # same padded size as case 0: keep the fixture small
+            d[f"c{i}_F"] = w2.data[0].data
+        print("  fft case", i, "padded", w2.data[0].data.shape, "shape_out", tuple(w2.shape))
+    d["n"] = np.array(len(cases))
+    d["scratch"] = np.array(lentil.propagate.scratch_shape([500e-9, 700e-9], 1 / 36, 5e-6, 10.0, 2))
+    np.savez_compressed(os.path.join(GOLD, "propagate_fft.npz"), **d)
+    print("propagate_fft: oracle == reference bit-for-bit on", len(cases), "cases")
+
+
 if __name__ == "__main__":
     assert lentil.__version__ == "0.8.8", lentil.__version__
     golden_dft2()
@@ -320,5 +355,6 @@ if __name__ == "__main__":
     golden_propagate()
     golden_detector()
     golden_dispersive_tilt()
+    golden_propagate_fft()
     sizes = {f: os.path.getsize(os.path.join(GOLD, f)) for f in sorted(os.listdir(GOLD))}
     print("fixtures:", sizes)

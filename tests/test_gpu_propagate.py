@@ -371,3 +371,49 @@ def test_phase_only_plane_and_explicit_nonbool_mask():
     assert peak_err(w.data[0].data, f[0]["data"]) <= 1e-15
     with pytest.raises(IndexError):
         lentil.Wavefront(600e-9) * lentil.Pupil(amplitude=np.zeros((8, 8)), opd=np.zeros((8, 8)), pixelscale=1, focal_length=1)
+
+
+# ---- propagate_fft (lentil/propagate.py:9-88): the FFT sibling, executed as a K2a launch -----------
+def test_propagate_fft_golden(golden):
+    d = golden("propagate_fft")
+    for i in range(int(d["n"])):
+        dx, z, du, os_ = float(d[f"c{i}_dx"]), float(d[f"c{i}_z"]), float(d[f"c{i}_du"]), int(d[f"c{i}_os"])
+        shape = None if d[f"c{i}_shape"][0] < 0 else tuple(int(v) for v in d[f"c{i}_shape"])
+        p = lentil.Pupil(amplitude=d[f"c{i}_amp"], opd=d[f"c{i}_opd"], pixelscale=dx, focal_length=z)
+        w = lentil.propagate_fft(lentil.Wavefront(float(d[f"c{i}_wl"])) * p, pixelscale=du, shape=shape,
+                                 oversample=os_)
+        assert tuple(int(v) for v in w.shape) == tuple(int(v) for v in d[f"c{i}_shape_out"])
+        assert w.wavelength == float(d[f"c{i}_prop_wl"])
+        assert w.ptype == lentil.image and len(w.data) == 1
+        if f"c{i}_F" in d:
+            assert tuple(w.data[0].shape) == d[f"c{i}_F"].shape
+            assert peak_err(w.data[0].data, d[f"c{i}_F"]) <= TOL64
+        assert peak_err(w.intensity, d[f"c{i}_intensity"]) <= TOL64
+
+
+def test_propagate_fft_errors_and_scratch():
+    amp = synth.normalize_power(synth.annulus((32, 32), 14))
+    w = lentil.Wavefront(650e-9) * lentil.Pupil(amplitude=amp, pixelscale=1 / 28, focal_length=10.0)
+    with pytest.raises(ValueError):
+        lentil.propagate_fft(w, pixelscale=5e-6, shape=(4000, 4000), oversample=2)
+    with pytest.raises(ValueError):
+        lentil.propagate_fft(w, pixelscale=5e-6, shape=(8, 8), scratch=np.zeros((16, 16), dtype=complex))
+    big = np.zeros(tuple(v + 1 for v in lentil.scratch_shape(650e-9, 1 / 28, 5e-6, 10.0, 2)), dtype=complex)
+    a = lentil.propagate_fft(w, pixelscale=5e-6, shape=(8, 8), scratch=big).intensity
+    b = lentil.propagate_fft(w, pixelscale=5e-6, shape=(8, 8)).intensity
+    assert np.array_equal(a, b)
+    pl = lentil.Pupil(amplitude=amp, opd=np.fromfunction(lambda r, c: 1e-7 * r, (32, 32)), pixelscale=1 / 28,
+                      focal_length=10.0).fit_tilt()
+    with pytest.raises(NotImplementedError):
+        lentil.propagate_fft(lentil.Wavefront(650e-9) * pl, pixelscale=5e-6, shape=(8, 8))
+
+
+def test_propagate_fft_equals_dft_at_the_fft_sampling():
+    # at the wavelength the integer padding really samples, both propagators evaluate the same sum
+    amp = synth.normalize_power(synth.annulus((64, 64), 30, 0.3))
+    p = lentil.Pupil(amplitude=amp, pixelscale=1 / 60, focal_length=10.0)     # flat: phasor independent of wavelength
+    wf = lentil.propagate_fft(lentil.Wavefront(640e-9) * p, pixelscale=5e-6, shape=(24, 24), oversample=2)
+    wd = lentil.propagate_dft(lentil.Wavefront(wf.wavelength) * p, pixelscale=5e-6, shape=(24, 24), oversample=2)
+    assert wf.field.shape == wd.field.shape == (48, 48)
+    assert peak_err(wf.field, wd.field) <= 1e-9
+    assert peak_err(wf.intensity, wd.intensity) <= 1e-9

@@ -262,3 +262,35 @@ def test_dispersive_tilt_in_propagation_shift_chain():
     x, y = dt.__shift__(wavelength=700e-9)
     r, c = w.data[0].shift(z=10.0, wavelength=700e-9, pixelscale=(5e-6, 5e-6), oversample=2)
     assert np.isclose(r, -y / 5e-6 * 2) and np.isclose(c, x / 5e-6 * 2)
+
+
+def test_fft_geometry_equals_padded_shifted_fft():
+    # propagate_fft never builds the padded array: the dft2 offset/shift it hands to K2a must make
+    # the matrix transform of the surviving rows equal ifftshift(fft2(fftshift(pad(x)))) for even
+    # and odd padded sizes, pads and crops (lentil/propagate.py:83-84,135-136, util.py:31-90)
+    from lentil_b200.propagate import _padded_fft_geometry
+    rng = np.random.default_rng(0)
+    for have, npix in [((20, 20), (32, 32)), ((21, 20), (33, 31)), ((20, 21), (31, 32)),
+                       ((40, 41), (32, 31)), ((33, 33), (33, 33)), ((10, 11), (11, 10))]:
+        x = rng.normal(size=have) + 1j * rng.normal(size=have)
+        ref = np.fft.ifftshift(np.fft.fft2(np.fft.fftshift(oc.pad(x, npix)), norm='ortho'))
+        r0, nr, off_r, odd_r = _padded_fft_geometry(have[0], npix[0])
+        c0, nc, off_c, odd_c = _padded_fft_geometry(have[1], npix[1])
+        F = oc.dft2(x[r0:r0 + nr, c0:c0 + nc], (1 / npix[0], 1 / npix[1]), shape=npix,
+                    shift=(odd_r, odd_c), offset=(off_r, off_c))
+        assert np.max(np.abs(F - ref)) <= 1e-13 * np.max(np.abs(ref))
+
+
+def test_scratch_shape_and_fft_shape(golden):
+    d = golden("propagate_fft")
+    assert tuple(lentil.scratch_shape([500e-9, 700e-9], 1 / 36, 5e-6, 10.0, 2)) == tuple(d["scratch"])
+    from lentil_b200.propagate import _fft_shape
+    npix, pw = _fft_shape(np.array([1 / 36, 1 / 36]), np.array([5e-6, 5e-6]), 10.0, 650e-9, 2)
+    onpix, opw = oc.fft_shape(np.array([1 / 36, 1 / 36]), np.array([5e-6, 5e-6]), 10.0, 650e-9, 2)
+    assert tuple(npix) == tuple(onpix) and pw == opw
+
+
+def test_propagate_fft_refuses_tilt_before_touching_the_device():
+    w = lentil.Wavefront(650e-9, tilt=[1e-6, 0])
+    with pytest.raises(NotImplementedError):
+        lentil.propagate_fft(w, pixelscale=5e-6, shape=(8, 8))

@@ -114,3 +114,33 @@ def test_detector_golden(golden):
     assert np.array_equal(oc.rebin(d["cube"], 2), d["rebin_cube2"])
     assert np.array_equal(oc.pixel(d["img"], 2), d["pixel2"])
     assert np.array_equal(oc.pixel(d["img"][:45, :45], 3), d["pixel3"])
+
+
+def test_propagate_fft_golden(golden):
+    # oracle restatement of lentil/propagate.py:9-88 against what the reference produced
+    d = golden("propagate_fft")
+    for i in range(int(d["n"])):
+        amp, opd, wl = d[f"c{i}_amp"], d[f"c{i}_opd"], float(d[f"c{i}_wl"])
+        dx, z, du, os_ = float(d[f"c{i}_dx"]), float(d[f"c{i}_z"]), float(d[f"c{i}_du"]), int(d[f"c{i}_os"])
+        shape = None if d[f"c{i}_shape"][0] < 0 else tuple(int(v) for v in d[f"c{i}_shape"])
+        fields = oc.plane_multiply([oc.make_field(np.array(1, dtype=complex))], amp, opd, None, wl)
+        F, shape_out, pw = oc.propagate_fft(fields, amp.shape, wl, (dx, dx), z, du, shape, os_)
+        assert tuple(shape_out) == tuple(d[f"c{i}_shape_out"]) and pw == float(d[f"c{i}_prop_wl"])
+        if f"c{i}_F" in d:
+            assert np.array_equal(F["data"], d[f"c{i}_F"])
+        assert np.array_equal(oc.wavefront_intensity([F], shape_out), d[f"c{i}_intensity"])
+
+
+def test_propagate_fft_refuses_tilt_and_oversized_shape():
+    f = oc.make_field(np.ones((8, 8)), None, [oc.tilt_entry(1e-6, 0)])
+    try:
+        oc.propagate_fft([f], (8, 8), 600e-9, (1 / 8, 1 / 8), 10.0, 5e-6, (4, 4), 2)
+        assert False
+    except NotImplementedError:
+        pass
+    g = oc.make_field(np.ones((8, 8)))
+    try:
+        oc.propagate_fft([g], (8, 8), 600e-9, (1 / 8, 1 / 8), 10.0, 5e-6, (4000, 4000), 2)
+        assert False
+    except ValueError:
+        pass
