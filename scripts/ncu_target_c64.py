@@ -9,7 +9,7 @@ from lentil_b200 import _lib, device  # noqa: E402
 
 L = _lib.lib()
 dev = device.device()
-B, m, M = 16, 1001, 1024
+B, m, M = int(os.environ.get("LFD_B", "16")), 1001, 1024
 f = torch.randn(B, m, m, 2, dtype=torch.float32, device=dev)
 o = torch.empty(B, M, M, 2, dtype=torch.float32, device=dev)
 descs = (_lib.MftDesc * B)()
