@@ -64,6 +64,9 @@ constexpr int ACC_COLS = 4 * NR;               // TMEM columns of the accumulato
 constexpr int A_STAGE_COLS = 32;               // 4 planes x 8 K
 static_assert(ACC_COLS + NA * A_STAGE_COLS <= 512, "TMEM budget");
 static_assert(NB == 12 && NA == 4, "the issuer's loop is unrolled over lcm(NA, NB) = 12 blocks, and 12 / NA must be odd");
+#ifndef LFD_PROD_NS
+#define LFD_PROD_NS 100
+#endif
 constexpr int NSETS = 2;                 // generator sets of four warps; set p makes the twiddles of k-blocks jb = p (mod NSETS)
 constexpr int MMA_WARP = 0, PROD_WARP = 1 + 4 * NSETS;
 constexpr int NTHREADS = 32 * (2 + 4 * NSETS);   // MMA warp + generators (warps 1 .. 4 NSETS) + bulk-copy producer warp
@@ -460,7 +463,7 @@ mft_c64_kernel(const CStage *__restrict__ descs) {
             const unsigned char *src = d.B + ((long long)tc * nkb + kb0) * B_BYTES;
             for (int jb = 0; jb < nblk; ++jb) {
                 const int sl = jb % NB;
-                if (jb >= NB) mbar_wait_sleep(&emptyB_bar[sl], ((jb / NB) - 1) & 1, 100);
+                if (jb >= NB) mbar_wait_sleep(&emptyB_bar[sl], ((jb / NB) - 1) & 1, LFD_PROD_NS);
                 const uint32_t bar = smem_u32(&fullB_bar[sl]);
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)B_BYTES) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
