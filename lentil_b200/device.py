@@ -39,9 +39,15 @@ def set_device(index):
     return _device
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr():
     """cudaStream_t of torch's current stream, as an int for ctypes."""
-    return torch.cuda.current_stream(device()).cuda_stream
+    dev = device()
+    if _raw_stream is not None:
+        return _raw_stream(dev.index)
+    return torch.cuda.current_stream(dev).cuda_stream
 
 
 def is_dev(x):

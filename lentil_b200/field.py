@@ -122,7 +122,8 @@ class Field:
         x, y = 0, 0
         for t in self.tilt:
             x, y = t.__shift__(xs=x, ys=y, z=z, wavelength=wavelength)
-        pixelscale = np.broadcast_to(pixelscale, (2,))
+        if np.ndim(pixelscale) == 0:
+            pixelscale = (pixelscale, pixelscale)
         out = x / pixelscale[0] * oversample, y / pixelscale[1] * oversample
         if indexing == 'ij':
             out = -out[1], out[0]

@@ -12,8 +12,27 @@ from . import _lib, device
 
 
 def _pair(v):
-    a, b = np.broadcast_to(v, (2,))
+    if np.ndim(v) == 0:
+        return v, v
+    a, b = v
     return a, b
+
+
+_workspaces = {}
+
+
+def _workspace(nbytes):
+    """Grow-only scratch buffer per CUDA stream: launches on one stream are ordered, so the planes of the next
+    call may reuse the intermediates of the previous one (saves an allocation per call of the drop-in loop)."""
+    if nbytes > (256 << 20):            # big batches: leave it to torch's caching allocator
+        return device.empty_bytes(nbytes)
+    key = device.stream_ptr()
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        if len(_workspaces) > 8:
+            _workspaces.clear()
+        ws = _workspaces[key] = device.empty_bytes(max(nbytes, 1 << 20))
+    return ws
 
 
 def mft_descriptor(desc, f_dev, out_dev, alpha, shift, offset, unitary=True, inverse=False):
@@ -64,12 +83,12 @@ def run_mft(descs, count, precision='c128', pupil_src=None, intensity_out=False)
     L = _lib.lib()
     if precision == 'c64':
         need = L.lfd_mft_c64x3_workspace_bytes(descs, count)
-        ws = device.empty_bytes(need)
+        ws = _workspace(need)
         _lib.check(L.lfd_mft_c64x3_batched(descs, count, ws.data_ptr(), need, device.stream_ptr()),
                    "lfd_mft_c64x3_batched")
         return ws
     need = L.lfd_mft_workspace_bytes(descs, count)
-    ws = device.empty_bytes(need)
+    ws = _workspace(need)
     if TIMERS is not None:
         import torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

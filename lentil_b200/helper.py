@@ -42,3 +42,14 @@ def mesh(shape, shift=(0, 0)):
     rr, cc = np.meshgrid(np.arange(shape[0]) - np.floor(shape[0] / 2.0) - shift[0],
                          np.arange(shape[1]) - np.floor(shape[1] / 2.0) - shift[1], indexing='ij')
     return rr, cc
+
+
+def pair(value):
+    """(2,) float/int array from a scalar or a pair — what np.broadcast_to(value, (2,)) gives, without the
+    stride-tricks overhead (this sits on the per-wavelength path of the drop-in loop)."""
+    if isinstance(value, np.ndarray) and value.shape == (2,):
+        return value
+    a = np.asarray(value)
+    if a.ndim == 0:
+        return np.array([a, a])
+    return a if a.shape == (2,) else np.broadcast_to(a, (2,))

@@ -12,6 +12,7 @@ host and executed as K1 -> K2a -> K3 over whole chunks of planes, with the pupil
 HBM and the PSF stack accumulated on the device.
 """
 import ctypes as C
+import math
 
 import numpy as np
 
@@ -66,19 +67,19 @@ def plan_window(shift, prop_shape_out, out_extent):
     shift : (r, c) float pixel shift of the field centre in the output plane.
     Returns None when the propagation window misses the output region, else
     ``(intersect_shape, intersect_shift, dft_shift)``: the window to compute, the offset of the
-    resulting Field, and the shift handed to dft2 (= prop_shift + sub-pixel remainder)."""
-    shift = np.asarray(shift, dtype=float)
-    fix_shift = np.fix(shift)
-    subpx_shift = shift - fix_shift
-    prop_extent = _extent.array_extent(prop_shape_out, fix_shift)
+    resulting Field, and the shift handed to dft2 (= prop_shift + sub-pixel remainder).
+    Plain Python arithmetic (this runs once per Field and wavelength in the drop-in loop);
+    math.trunc is np.fix for finite floats."""
+    sr, sc = float(shift[0]), float(shift[1])
+    fr, fc = float(math.trunc(sr)), float(math.trunc(sc))
+    prop_extent = _extent.array_extent(prop_shape_out, (fr, fc))
     if not _extent.intersect(out_extent, prop_extent):
         return None
     intersect_shape = _extent.intersection_shape(out_extent, prop_extent)
     intersect_shift = _extent.intersection_shift(out_extent, prop_extent)
     intersect_extent = _extent.array_extent(intersect_shape, intersect_shift)
-    prop_shift = (np.array(_extent.array_center(prop_extent))
-                  - np.array(_extent.array_center(intersect_extent)))
-    return intersect_shape, intersect_shift, prop_shift + subpx_shift
+    pc, ic = _extent.array_center(prop_extent), _extent.array_center(intersect_extent)
+    return intersect_shape, intersect_shift, np.array([pc[0] - ic[0] + (sr - fr), pc[1] - ic[1] + (sc - fc)])
 
 
 def propagate_dft(wavefront, pixelscale, shape=None, prop_shape=None, oversample=2, mask=None):
@@ -89,14 +90,14 @@ def propagate_dft(wavefront, pixelscale, shape=None, prop_shape=None, oversample
     whose `data` holds one Field per input Field that lands on the output (possibly none)."""
     ptype_out = _propagate_ptype(wavefront.ptype, method='fraunhofer')
 
-    shape = np.asarray(wavefront.shape) if shape is None else np.broadcast_to(shape, (2,))
-    prop_shape = np.asarray(shape) if prop_shape is None else np.broadcast_to(prop_shape, (2,))
+    shape = np.asarray(wavefront.shape) if shape is None else helper.pair(shape)
+    prop_shape = np.asarray(shape) if prop_shape is None else helper.pair(prop_shape)
     shape_out = shape * oversample
     prop_shape_out = prop_shape * oversample
     out_extent = _output_extent(shape_out, mask)
 
     dx = wavefront.pixelscale
-    du = np.broadcast_to(pixelscale, (2,))
+    du = helper.pair(pixelscale)
     z = wavefront.focal_length
 
     out = Wavefront.empty(wavelength=wavefront.wavelength, pixelscale=du / oversample,

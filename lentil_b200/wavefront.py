@@ -12,6 +12,7 @@ import importlib
 import numpy as np
 
 from . import device
+from . import helper as _helper
 from . import field as _field
 from .field import Field
 
@@ -21,7 +22,7 @@ _WAVEFRONT_PTYPES = (_pt.none, _pt.pupil, _pt.image)
 
 
 def _as_pair(value):
-    return None if value is None else np.broadcast_to(value, (2,))
+    return None if value is None else _helper.pair(value)
 
 
 class Wavefront:
