@@ -44,6 +44,8 @@ ptilt = [(t.x, t.y) for t in p.tilt]
 ref = oc.psf(p.amplitude, p.opd, cube, wls[:1], [1.0], (dx, dx), z, du, (256, 256), None, 2, plane_tilt=ptilt)
 got = lentil.propagate_dft_batch(p, wls[:1], du, (256, 256), oversample=2)
 print("cfg3 parity (1 wavelength):", float(np.max(np.abs(got - ref)) / np.max(ref)))
+dt32, img32 = timed(lambda: lentil.propagate_dft_batch(p, wls, du, (256, 256), oversample=2, weights=np.full(50, 0.02), precision='c64'))
+print(f"cfg3 c64: {dt32*1e3:.1f} ms per PSF ({900/dt32:.0f} windows/s), PSF error vs FP64 {float(np.max(np.abs(img32 - img)) / np.max(img)):.2e}")
 
 # ---- config 4: 512^2 pupil -> 256^2 det x os2, realisations x 32 wavelengths (x3 diversity folded into realisations)
 mask = synth.circle((512, 512), 250)
@@ -60,6 +62,9 @@ print(f"cfg4: {R} realisations x 32 wavelengths = {R*32} planes of 501^2->512^2:
 ref = oc.psf(amp, opds[3], None, wl4[:2], [0.5, 0.5], (1 / 500, 1 / 500), 20.0, 5e-6, (256, 256), None, 2)
 got = lentil.propagate_dft_batch(p4, wl4[:2], 5e-6, (256, 256), oversample=2, weights=[0.5, 0.5], opds=opds[3:4])
 print("cfg4 parity:", float(np.max(np.abs(got[0] - ref)) / np.max(ref)))
+dt32, st32 = timed(lambda: lentil.propagate_dft_batch(p4, wl4, 5e-6, (256, 256), oversample=2, weights=np.full(32, 1 / 32),
+                                                       opds=opds_dev, return_device=True, precision='c64'))
+print(f"cfg4 c64: {dt32*1e3:.1f} ms ({R*32/dt32:.0f} planes/s), PSF error vs FP64 {float((st32 - st).abs().max() / st.max()):.2e}")
 
 # ---- config 5: 4096^2 pupil -> 1024^2 det x os2, wavelengths x 16 field points
 mask = synth.annulus((4096, 4096), 2040)
@@ -76,3 +81,6 @@ print(f"cfg5: 4 wavelengths x 16 field points = 64 planes of 4081^2->2048^2: {dt
 ref = oc.psf(amp, opd, None, wl5[:1], [1.0], (1 / 4080, 1 / 4080), 20.0, 5e-6, (1024, 1024), None, 2, wf_tilt=tilts[5])
 got = lentil.propagate_dft_batch(p5, wl5[:1], 5e-6, (1024, 1024), oversample=2, tilts=[tilts[5]])
 print("cfg5 parity (1 plane):", float(np.max(np.abs(got[0] - ref)) / np.max(ref)))
+dt32, st32 = timed(lambda: lentil.propagate_dft_batch(p5, wl5, 5e-6, (1024, 1024), oversample=2, weights=np.full(4, 0.25),
+                                                       tilts=tilts, return_device=True, precision='c64'), reps=1)
+print(f"cfg5 c64: {dt32*1e3:.0f} ms ({64/dt32:.1f} planes/s), PSF error vs FP64 {float((st32 - st).abs().max() / st.max()):.2e}")
