@@ -73,25 +73,18 @@ def to_dev(arr, dtype=None):
     return t.to(device(), non_blocking=True)
 
 
-_pinned = {}
-
-
 def to_host(t):
-    """Device tensor -> fresh numpy array.  Large transfers are staged through a cached pinned
-    buffer (async D2H at full PCIe rate, then one host memcpy)."""
+    """Device tensor -> fresh numpy array.  Large transfers land in a pinned buffer from torch's caching host
+    allocator (async D2H at full PCIe rate) that the returned array owns: no second host copy, and the block goes
+    back to the allocator's cache when the array is dropped."""
     t = t.detach()
     nbytes = t.numel() * t.element_size()
     if nbytes < (1 << 20) or not t.is_contiguous():
         return t.cpu().numpy()
-    key = (t.dtype, t.numel())
-    pin = _pinned.get(key)
-    if pin is None:
-        if len(_pinned) > 8:
-            _pinned.clear()
-        pin = _pinned[key] = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
-    pin.copy_(t.reshape(-1), non_blocking=True)
+    pin = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    pin.copy_(t, non_blocking=True)
     torch.cuda.current_stream(t.device).synchronize()
-    return pin.numpy().reshape(tuple(t.shape)).copy()
+    return pin.numpy()
 
 
 def ld_of(t):
