@@ -104,6 +104,11 @@ int lfd_mft_c128_from_pupil(const lfd_mft_desc *descs_host, const lfd_pupil_src 
 size_t lfd_mft_c64x3_workspace_bytes(const lfd_mft_desc *descs_host, int count);
 int lfd_mft_c64x3_batched(const lfd_mft_desc *descs_host, int count,
                           void *workspace_dev, size_t workspace_bytes, void *stream);
+/* K1 fused into K2b, the complex64 twin of lfd_mft_c128_from_pupil: desc.f / ldf are ignored, the fold kernel forms
+ * amp * mask * exp(+2 pi i opd / lambda) itself (phase reduced in float64, phasor rounded to complex64;
+ * lentil/plane.py:502-507).  With intensity_out != 0 desc.out receives |F|^2 as float64 (ldo in doubles). */
+int lfd_mft_c64x3_from_pupil(const lfd_mft_desc *descs_host, const lfd_pupil_src *src_host, int count,
+                             int intensity_out, void *workspace_dev, size_t workspace_bytes, void *stream);
 
 /* ---- K1: pupil prep ------------------------------------------------------------------
  * For each wavelength w and segment s:  out_{w,s}[r,c] = amp[r,c] * mask_s[r,c] *

@@ -71,6 +71,8 @@ SIGNATURES = {
                                           C.c_size_t, C.c_void_p]),
     "lfd_mft_c64x3_workspace_bytes": (C.c_size_t, [C.POINTER(MftDesc), C.c_int]),
     "lfd_mft_c64x3_batched": (C.c_int, [C.POINTER(MftDesc), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "lfd_mft_c64x3_from_pupil": (C.c_int, [C.POINTER(MftDesc), C.POINTER(PupilSrc), C.c_int, C.c_int, C.c_void_p,
+                                          C.c_size_t, C.c_void_p]),
     "lfd_pupil_prep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                  C.POINTER(Segment), C.c_int32, C.POINTER(C.c_double), C.c_int32,
                                  C.c_void_p, C.c_int64, C.c_void_p]),

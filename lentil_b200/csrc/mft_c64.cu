@@ -93,6 +93,7 @@ struct CStage {
     unsigned char *nB; long long nplane;   // FOLD_OUT: next stage's pre-blocked data operand
     int nKf, nKpad, nhm, ncR2, nKfp, ntile;
     const int *kmax;                       // row stage: support map of its input (NULL: all K blocks)
+    int intensity, pad3_;                  // final stage: write |F|^2 as float64 (ldo in doubles) instead of the complex64 field
     double alpha, oprime, sprime, scale, nalpha, nsprime;
 };
 
@@ -273,8 +274,27 @@ struct FoldSplit {
     int nhm, ncR2, nKf, slots;       // slots = Npad / 2
     double alpha, sprime, sgn;
     int *kmax;                       // support map, as in mft_folded.cu: [tile] = 1 + last row with data,
-    int ntile, pad_;                 // [ntile + tile] = Kf - first row with data (column tile = 32 slots)
+    int ntile, pad_;                 // [ntile + tile] = Kf - first row with data (column tile = TN slots)
+    // fused pupil prep (K1 inside the fold, as in mft_folded.cu): when amp != NULL the input element (i, c) is not read
+    // from D but formed as amp * mask * exp(+2 pi i opd / lambda) at pupil pixel (pr0 + i, pc0 + c), lentil/plane.py:502-507
+    const double *amp, *opd;
+    const unsigned char *mask;       // this segment's mask plane, or NULL
+    long long pld;                   // pupil row stride (n_c)
+    int pr0, pc0;
+    double wavelength;
 };
+
+// the phase is reduced in fp64 (in cycles) before the sine/cosine, the phasor is then rounded to complex64
+__device__ __forceinline__ float2 pupil_phasor_c64(const FoldSplit &d, int i, int c) {
+    const long long pix = (long long)(d.pr0 + i) * d.pld + (d.pc0 + c);
+    double a = d.amp[pix];
+    if (d.mask != nullptr && d.mask[pix] == 0) a = 0.0;
+    if (a == 0.0) return make_float2(0.f, 0.f);
+    const double tcyc = d.opd[pix] / d.wavelength;
+    double sn, cs;
+    sincospi(2.0 * (tcyc - rint(tcyc)), &sn, &cs);
+    return make_float2((float)(a * cs), (float)(a * sn));
+}
 
 __global__ void __launch_bounds__(256)
 fold_split_kernel(const FoldSplit *__restrict__ descs) {
@@ -313,13 +333,14 @@ fold_split_kernel(const FoldSplit *__restrict__ descs) {
             if (col_ok && r < d.Kf) {
                 const int ip = d.hm + r, im = d.hm - r - d.cR2;
                 const float2 p = pre[rr];
-                float2 a = (ip < d.K) ? d.D[(long long)ip * d.ldd + j] : make_float2(0.f, 0.f);
+                const bool pupil = d.amp != nullptr;
+                float2 a = (ip < d.K) ? (pupil ? pupil_phasor_c64(d, ip, j) : d.D[(long long)ip * d.ldd + j]) : make_float2(0.f, 0.f);
                 const float gpr = a.x * p.x - a.y * p.y, gpi = a.x * p.y + a.y * p.x;
                 bool nz = (a.x != 0.f) || (a.y != 0.f);
                 if (d.cR2 == 0 && r == 0) {
                     ger = gpr; gei = gpi;
                 } else {
-                    float2 b = d.D[(long long)im * d.ldd + j];
+                    float2 b = pupil ? pupil_phasor_c64(d, im, j) : d.D[(long long)im * d.ldd + j];
                     nz = nz || (b.x != 0.f) || (b.y != 0.f);
                     const float gmr = b.x * p.x + b.y * p.y, gmi = b.y * p.x - b.x * p.y;
                     ger = gpr + gmr; gei = gpi + gmi; gor = gpr - gmr; goi = gpi - gmi;
@@ -568,6 +589,12 @@ mft_c64_kernel(const CStage *__restrict__ descs) {
                     const float Ai = __uint_as_float(am[2 * i + 1]) + __uint_as_float(ac[2 * i + 1]);
                     const float Br = sg * (__uint_as_float(bm[2 * i]) + __uint_as_float(bc[2 * i]));
                     const float Bi = sg * (__uint_as_float(bm[2 * i + 1]) + __uint_as_float(bc[2 * i + 1]));
+                    if (d.intensity) {      // |post|^2 = scale^2 is folded into the squared modulus of the rotated value
+                        double *col = (double *)d.out + (long long)c * d.ldo;
+                        if (has_p) { const float xr = Ar - Bi, xi = Ai + Br, yr = xr * ppc - xi * pps, yi = xr * pps + xi * ppc; col[kp] = (double)yr * yr + (double)yi * yi; }
+                        if (has_m) { const float xr = Ar + Bi, xi = Ai - Br, yr = xr * pmc - xi * pms, yi = xr * pms + xi * pmc; col[km] = (double)yr * yr + (double)yi * yi; }
+                        continue;
+                    }
                     float2 *col = d.out + (long long)c * d.ldo;
                     if (has_p) { const float xr = Ar - Bi, xi = Ai + Br; col[kp] = make_float2(xr * ppc - xi * pps, xr * pps + xi * ppc); }
                     if (has_m) { const float xr = Ar + Bi, xi = Ai - Br; col[km] = make_float2(xr * pmc - xi * pms, xr * pms + xi * pmc); }
@@ -700,7 +727,7 @@ size_t c64_workspace_bytes(const lfd_mft_desc *descs, int count) {
 }
 
 int launch_mft_c64(const lfd_mft_desc *descs, int count, void *workspace, size_t workspace_bytes,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, const lfd_pupil_src *src = nullptr, int intensity_out = 0) {
     if (count == 0) return 0;
     LFD_REQUIRE(descs && workspace, "lfd_mft_c64x3_batched: NULL argument");
     LFD_REQUIRE(count <= 32767, "lfd_mft_c64x3_batched: at most 32767 planes per call (got %d)", count);
@@ -724,7 +751,9 @@ int launch_mft_c64(const lfd_mft_desc *descs, int count, void *workspace, size_t
     int max_tab = 0, max_t1 = 0, max_t2 = 0, max_fs_x = 0, max_fs_y = 0;
     for (int i = 0; i < count; ++i) {
         const lfd_mft_desc &p = descs[i];
-        if (!(p.m > 0 && p.n > 0 && p.M > 0 && p.N > 0 && p.ldf >= p.n && p.ldo >= p.N && p.f && p.out)) {
+        const bool src_ok = !src || (src[i].amp && src[i].opd && src[i].wavelength != 0.0 && src[i].r0 >= 0 && src[i].c0 >= 0 &&
+                                     src[i].r0 + p.m <= src[i].n_r && src[i].c0 + p.n <= src[i].n_c);
+        if (!(p.m > 0 && p.n > 0 && p.M > 0 && p.N > 0 && (src || (p.ldf >= p.n && p.f)) && p.ldo >= p.N && p.out && src_ok)) {
             free(h);
             LFD_REQUIRE(false, "lfd_mft_c64x3_batched: plane %d has invalid shape/ld/pointers", i);
         }
@@ -748,6 +777,10 @@ int launch_mft_c64(const lfd_mft_desc *descs, int count, void *workspace, size_t
         f.permute = 1; f.nhm = p.n / 2; f.ncR2 = cRn; f.nKf = g.Kf2; f.slots = g.slots1;
         f.alpha = p.alpha_r; f.sprime = p.shift_r + 0.5 * cUM; f.sgn = sgn;
         f.kmax = kmax_dev; f.ntile = g.slots1 / TN; f.pad_ = 0;
+        if (src) {
+            f.amp = src[i].amp; f.opd = src[i].opd; f.mask = src[i].mask;
+            f.pld = src[i].n_c; f.pr0 = src[i].r0; f.pc0 = src[i].c0; f.wavelength = src[i].wavelength;
+        }
         if (g.slots1 / TN > max_fs_x) max_fs_x = g.slots1 / TN;
         if (g.Kpad1 / 32 > max_fs_y) max_fs_y = g.Kpad1 / 32;
 
@@ -768,7 +801,7 @@ int launch_mft_c64(const lfd_mft_desc *descs, int count, void *workspace, size_t
         s2.Rf = g.Rf2; s2.M = p.N; s2.hM = p.N / 2; s2.cR2 = cRn; s2.cU2 = cUN; s2.Rfp = g.Rfp2;
         s2.tiles_r = g.Rfp2 / TM; s2.tiles_c = g.Npad2 / NR;
         s2.sgn = sgn; s2.tabd = td2; s2.tabf = tf2;
-        s2.out = (float2 *)p.out; s2.ldo = p.ldo; s2.nB = nullptr; s2.nplane = 0;
+        s2.out = (float2 *)p.out; s2.ldo = p.ldo; s2.nB = nullptr; s2.nplane = 0; s2.intensity = intensity_out;
         s2.nKf = 0; s2.nKpad = 0; s2.nhm = 0; s2.ncR2 = 0; s2.nKfp = 0;
         s2.alpha = p.alpha_c; s2.oprime = p.off_c - 0.5 * cRn; s2.sprime = p.shift_c + 0.5 * cUN; s2.scale = scale;
         s2.nalpha = 0.0; s2.nsprime = 0.0; s2.kmax = nullptr; s2.ntile = 0;
@@ -809,6 +842,12 @@ extern "C" size_t lfd_mft_c64x3_workspace_bytes(const lfd_mft_desc *descs, int c
 extern "C" int lfd_mft_c64x3_batched(const lfd_mft_desc *descs, int count, void *workspace,
                                      size_t workspace_bytes, void *stream) {
     return lfd::c64::launch_mft_c64(descs, count, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int lfd_mft_c64x3_from_pupil(const lfd_mft_desc *descs, const lfd_pupil_src *src, int count, int intensity_out,
+                                        void *workspace, size_t workspace_bytes, void *stream) {
+    LFD_REQUIRE(descs && src && workspace && count > 0, "lfd_mft_c64x3_from_pupil: bad arguments");
+    return lfd::c64::launch_mft_c64(descs, count, workspace, workspace_bytes, (cudaStream_t)stream, src, intensity_out);
 }
 
 #ifdef LFD_TILE_TIMING

@@ -79,13 +79,17 @@ def mft_flops_executed(descs, count):
 def run_mft(descs, count, precision='c128', pupil_src=None, intensity_out=False):
     """Launch a batch of planes on the current stream with a torch-owned workspace.
     precision 'c128': K2a (FP64 DMMA); 'c64': K2b (complex64 arrays, 3xTF32 on tcgen05).
-    pupil_src: optional lfd_pupil_src table — the fused K1+K2a entry point (folded variant, c128)."""
+    pupil_src: optional lfd_pupil_src table — the fused K1+K2 entry points (folded K2a, or K2b)."""
     L = _lib.lib()
     if precision == 'c64':
         need = L.lfd_mft_c64x3_workspace_bytes(descs, count)
         ws = _workspace(need)
-        _lib.check(L.lfd_mft_c64x3_batched(descs, count, ws.data_ptr(), need, device.stream_ptr()),
-                   "lfd_mft_c64x3_batched")
+        if pupil_src is not None:
+            _lib.check(L.lfd_mft_c64x3_from_pupil(descs, pupil_src, count, int(bool(intensity_out)), ws.data_ptr(), need,
+                                                  device.stream_ptr()), "lfd_mft_c64x3_from_pupil")
+        else:
+            _lib.check(L.lfd_mft_c64x3_batched(descs, count, ws.data_ptr(), need, device.stream_ptr()),
+                       "lfd_mft_c64x3_batched")
         return ws
     need = L.lfd_mft_workspace_bytes(descs, count)
     ws = _workspace(need)

@@ -317,9 +317,9 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
         lam = wavelengths[cl]
         nw = len(lam)
         # With one field point every phasor feeds exactly one transform: K1 is then fused into the fold
-        # kernel of the folded K2a (lfd_mft_c128_from_pupil) and phasors never exist in HBM; with a single
+        # kernel of the folded K2a / of K2b (lfd_mft_c128_from_pupil, lfd_mft_c64x3_from_pupil) and phasors never exist in HBM; with a single
         # segment the column stage also squares the field itself (no coherent merge to do in K3).
-        fused = (not c64) and P == 1 and _lib.lib().lfd_get_mft_variant() == 1
+        fused = P == 1 and (c64 or _lib.lib().lfd_get_mft_variant() == 1)
         intensity_out = fused and nseg == 1
         if not fused:
             phasors = torch.empty(nw, ops['total'], dtype=cdtype, device=device.device())

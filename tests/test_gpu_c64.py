@@ -70,3 +70,35 @@ def test_batch_pipeline_c64_against_oracle():
         assert peak_err(ref64[k], ref) <= 1e-10
     with pytest.raises(ValueError):
         lentil.propagate_dft_batch(p, wls, du, (128, 128), precision='fp16')
+
+
+def test_fused_pupil_prep_c64_single_field_point_and_segments():
+    """With one field point K1 is fused into K2b's fold kernel (lfd_mft_c64x3_from_pupil): monolithic pupils also take
+    the |F|^2 epilogue, segmented ones keep complex64 windows for the coherent merge in K3; a Monte-Carlo OPD stack
+    selects the OPD plane per realisation."""
+    from lentil_b200 import synth
+    rng = np.random.default_rng(9)
+    mask = synth.annulus((200, 200), 95, 0.25)
+    amp = synth.normalize_power(mask)
+    opd = synth.zernike_opd(mask, rng.normal(size=10) * 30e-9)
+    dx, z, du = 1 / 190, 15.0, 5e-6
+    wls, wts = np.linspace(550e-9, 800e-9, 5), np.array([0.1, 0.2, 0.4, 0.2, 0.1])
+    p = lentil.Pupil(amplitude=amp, opd=opd, pixelscale=dx, focal_length=z)
+    got = lentil.propagate_dft_batch(p, wls, du, (100, 100), oversample=2, weights=wts, precision='c64')
+    ref = oc.psf(amp, opd, None, wls, wts, (dx, dx), z, du, (100, 100), None, 2)
+    assert got.shape == ref.shape and peak_err(got, ref) <= TOL32
+    # Monte-Carlo realisations (one OPD plane each)
+    opds = np.stack([synth.zernike_opd(mask, rng.normal(size=10) * 25e-9) for _ in range(3)])
+    mc = lentil.propagate_dft_batch(p, wls[:2], du, (100, 100), oversample=2, weights=wts[:2], opds=opds, precision='c64')
+    for r in range(3):
+        assert peak_err(mc[r], oc.psf(amp, opds[r], None, wls[:2], wts[:2], (dx, dx), z, du, (100, 100), None, 2)) <= TOL32
+    # segmented pupil: windows overlap and must interfere
+    cube = synth.hex_segments(1, 30, 2)
+    sa = synth.normalize_power(cube.sum(axis=0).astype(float))
+    so = np.zeros(sa.shape)
+    for s in range(cube.shape[0]):
+        so += synth.zernike_opd(cube[s], rng.uniform(-1, 1, 3) * np.array([40e-9, 3e-7, 3e-7]))
+    ps = lentil.Pupil(amplitude=sa, opd=so, mask=cube, pixelscale=1 / 160, focal_length=12.0)
+    gs = lentil.propagate_dft_batch(ps, wls[:3], du, (64, 64), oversample=2, weights=wts[:3], precision='c64')
+    rs = oc.psf(sa, so, cube, wls[:3], wts[:3], (1 / 160, 1 / 160), 12.0, du, (64, 64), None, 2)
+    assert peak_err(gs, rs) <= TOL32
