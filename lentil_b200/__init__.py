@@ -13,7 +13,7 @@ there is no CPU fallback.
 __version__ = '0.1.0'
 
 from .ptype import ptype, none, pupil, image, tilt, transform  # noqa: F401
-from . import extent, helper, field, fourier, plane, propagate, wavefront, device, detector  # noqa: F401
+from . import extent, helper, field, fourier, plane, propagate, wavefront, device, detector, wfe  # noqa: F401
 from .field import Field  # noqa: F401
 from .plane import Plane, Pupil, Image, Tilt, DispersiveTilt, Grism  # noqa: F401
 from .wavefront import Wavefront  # noqa: F401
@@ -21,3 +21,4 @@ from .propagate import propagate_dft, propagate_dft_batch, propagate_fft, scratc
 from .helper import boundary  # noqa: F401
 from .device import set_device  # noqa: F401
 from .detector import rebin  # noqa: F401
+from .wfe import power_spectrum  # noqa: F401

@@ -493,3 +493,29 @@ def pixel(img, oversample=1):
     mtf_y = np.sinc(np.fft.fftfreq(img.shape[0]) * oversample)
     kernel = np.dot(mtf_x[:, np.newaxis], mtf_y[np.newaxis, :])
     return np.abs(np.fft.ifft2(np.fft.fft2(img) * kernel))
+
+
+# --------------------------------------------------------------------------------------------
+# wavefront-error generator of BASELINE config 5 (next row): lentil/wfe.py:8-70
+# --------------------------------------------------------------------------------------------
+
+
+def power_spectrum(mask, pixelscale, rms, half_power_freq, exp, seed=None):
+    """PSD-filtered random OPD, lentil/wfe.py:40-70 (same numpy calls in the same order)."""
+    mask = np.asarray(mask)
+    rng = np.random.default_rng(seed)
+    n, m = mask.shape
+    yy, xx = np.mgrid[0:m, 0:n]
+    yy = (yy - (np.floor(m / 2) + 1)) / m
+    xx = (xx - (np.floor(n / 2) + 1)) / n
+    dr = np.sqrt(xx * xx + yy * yy)
+    half_power_freq = half_power_freq * pixelscale / np.sqrt(m ** 2 + n ** 2)
+    psd = 1 / (1 + (dr / half_power_freq) ** exp)
+    psd[dr == 0] = 0
+    psd = psd / np.sum(psd)
+    H = np.fft.fftshift(np.sqrt(psd))
+    noise = rng.normal(size=[n, m])
+    opd = np.real(np.fft.ifft2(np.fft.fft2(noise) * H)) * np.sqrt(m * n)
+    opd *= mask
+    opd = opd * np.sqrt(np.count_nonzero(opd) / np.sum(np.abs(opd) ** 2)) * rms
+    return opd

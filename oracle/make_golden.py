@@ -347,6 +347,19 @@ def golden_propagate_fft():
     print("propagate_fft: oracle == reference bit-for-bit on", len(cases), "cases")
 
 
+def golden_power_spectrum():
+    d = {}
+    for i, (n, radius, seed) in enumerate([(48, 20, 3), (45, 19, 7)]):
+        mask = lentil.circle((n, n), radius, antialias=False)
+        args = dict(pixelscale=1 / (2 * radius), rms=30e-9, half_power_freq=5, exp=3, seed=seed)
+        ref = lentil.power_spectrum(mask, **args)
+        assert np.array_equal(oc.power_spectrum(mask, **args), ref)
+        d[f"c{i}_mask"], d[f"c{i}_opd"], d[f"c{i}_seed"], d[f"c{i}_radius"] = mask.astype(np.uint8), ref, np.array(seed), np.array(radius)
+    d["n"] = np.array(2)
+    np.savez_compressed(os.path.join(GOLD, "power_spectrum.npz"), **d)
+    print("power_spectrum: oracle == reference bit-for-bit (even and odd grid)")
+
+
 if __name__ == "__main__":
     assert lentil.__version__ == "0.8.8", lentil.__version__
     golden_dft2()
@@ -356,5 +369,6 @@ if __name__ == "__main__":
     golden_detector()
     golden_dispersive_tilt()
     golden_propagate_fft()
+    golden_power_spectrum()
     sizes = {f: os.path.getsize(os.path.join(GOLD, f)) for f in sorted(os.listdir(GOLD))}
     print("fixtures:", sizes)

@@ -70,3 +70,17 @@ def test_opd_synthesis_matches_einsum_and_feeds_the_batch():
     ref = oc.psf(p.amplitude, np.einsum('ijk,i->jk', basis, coeffs[4]), None, wls, wts, (1 / 90, 1 / 90), 20.0, 5e-6,
                  (48, 48), None, 2)
     assert peak_err(stack[4], ref) <= 1e-10
+
+
+def test_power_spectrum_golden(golden):
+    # lentil/wfe.py:8-70: the two FFTs of the noise shaping run as centred K2a transforms (even and odd grids)
+    d = golden("power_spectrum")
+    for i in range(int(d["n"])):
+        mask, ref = d[f"c{i}_mask"], d[f"c{i}_opd"]
+        opd = lentil.power_spectrum(mask, 1 / (2 * int(d[f"c{i}_radius"])), 30e-9, 5, 3, seed=int(d[f"c{i}_seed"]))
+        assert opd.shape == ref.shape
+        assert np.max(np.abs(opd - ref)) <= 1e-12 * np.max(np.abs(ref))
+        rms = np.sqrt(np.sum(opd ** 2) / np.count_nonzero(opd))
+        assert abs(rms - 30e-9) <= 1e-15
+    with pytest.raises(ValueError):
+        lentil.power_spectrum(np.ones((8, 9)), 1.0, 1e-9, 5, 3, seed=0)

@@ -144,3 +144,11 @@ def test_propagate_fft_refuses_tilt_and_oversized_shape():
         assert False
     except ValueError:
         pass
+
+
+def test_power_spectrum_golden(golden):
+    # oracle restatement of lentil/wfe.py:8-70 against the reference's output (same numpy generator, same FFT calls)
+    d = golden("power_spectrum")
+    for i in range(int(d["n"])):
+        opd = oc.power_spectrum(d[f"c{i}_mask"], 1 / (2 * int(d[f"c{i}_radius"])), 30e-9, 5, 3, seed=int(d[f"c{i}_seed"]))
+        assert np.array_equal(opd, d[f"c{i}_opd"])
