@@ -214,6 +214,28 @@ int lfd_abs_c128(const void *F_dev, int64_t ld, int32_t h, int32_t w, double *ou
 int lfd_opd_synth(const double *basis_dev, const double *coeffs_dev, const double *base_dev, int64_t npix,
                   int32_t K, int32_t R, int32_t accumulate, double *out_dev, void *stream);
 
+/* ---- spline rescale to native sampling ---------------------------
+ * lentil/util.py:261-347 (rescale) under lentil/detector.py:223-249 (pixelate); the reference calls
+ * scipy.ndimage.map_coordinates there (util.py:334-343).
+ * lfd_spline_prefilter: coef ((h+2*npad) x (w+2*npad), dense) = B-spline coefficients of the image padded
+ *   by npad edge samples; reflect != 0 selects the half-sample-symmetric boundary (map_coordinates modes
+ *   'nearest' and 'reflect'), 0 the whole-sample one ('mirror', 'constant', legacy 'wrap'). Orders 0 and 1
+ *   only pad. `scratch` has the size of `coef`.
+ * lfd_spline_eval: out[i,j] = sum_a sum_b coef[iy[i,a], ix[j,b]] * wy[i,a] * wx[j,b]; iy/wy are ny x ntaps,
+ *   ix/wx nx x ntaps (device).  nonzero != 0 reads the source as (v != 0) — the default mask of util.py:315-319.
+ * lfd_sum_f64: out[0] = sum of n doubles, fixed two-stage order; `partials` holds >= 256 doubles.
+ * lfd_rescale_finish: out = (re [+ i im]) * sum(img)/sum(out) * mask, mask < eps -> 0 (util.py:335-347).
+ *   sums = {Re sum(img), Im sum(img), Re sum(out), Im sum(out)} on the device or NULL (unitary=False);
+ *   im == NULL: real output (n doubles), else complex128 output (n elements); mask may be NULL. */
+int lfd_spline_prefilter(const double *img_dev, int64_t ld, int32_t h, int32_t w, int32_t npad, int32_t order,
+                         int32_t reflect, double *coef_dev, double *scratch_dev, void *stream);
+int lfd_spline_eval(const double *coef_dev, int64_t ld, int32_t nonzero, const int32_t *iy_dev, const double *wy_dev,
+                    int32_t ny, const int32_t *ix_dev, const double *wx_dev, int32_t nx, int32_t ntaps,
+                    double *out_dev, void *stream);
+int lfd_sum_f64(const double *x_dev, int64_t n, double *partials_dev, double *out_dev, void *stream);
+int lfd_rescale_finish(const double *re_dev, const double *im_dev, const double *mask_dev, const double *sums_dev,
+                       double eps, int64_t n, double *out_dev, void *stream);
+
 /* ---- host-buffer convenience layer (what bench.py's e2e leg and the numpy shim call) ------
  * A context owns a device workspace, pinned staging buffers and one stream on `device`.
  */

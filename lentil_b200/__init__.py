@@ -20,5 +20,5 @@ from .wavefront import Wavefront  # noqa: F401
 from .propagate import propagate_dft, propagate_dft_batch, propagate_fft, scratch_shape  # noqa: F401
 from .helper import boundary  # noqa: F401
 from .device import set_device  # noqa: F401
-from .detector import rebin  # noqa: F401
+from .detector import rebin, rescale  # noqa: F401
 from .wfe import power_spectrum  # noqa: F401

@@ -95,6 +95,13 @@ SIGNATURES = {
     "lfd_abs_c128": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "lfd_opd_synth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                 C.c_void_p]),
+    "lfd_spline_prefilter": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lfd_spline_eval": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                  C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "lfd_sum_f64": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lfd_rescale_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_void_p,
+                                     C.c_void_p]),
     "lfd_ctx_create": (C.c_void_p, [C.c_int]),
     "lfd_ctx_destroy": (None, [C.c_void_p]),
     "lfd_ctx_dft2_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,

@@ -496,6 +496,238 @@ def pixel(img, oversample=1):
 
 
 # --------------------------------------------------------------------------------------------
+# spline rescale to native sampling (next row): lentil/util.py:261-347 (rescale),
+# lentil/detector.py:223-249 (pixelate).  The interpolation itself lives in a third-party dependency
+# that is not vendored in the reference: scipy.ndimage.map_coordinates (scipy is unpinned in
+# pyproject.toml; checked here against scipy 1.18.1).  What follows restates its published algorithm
+# (Unser's recursive B-spline prefilter with exact boundary initialisation, then separable B-spline
+# evaluation) for the call sites of util.py:334-343, where the coordinates are a meshgrid of one x
+# vector and one y vector.
+# --------------------------------------------------------------------------------------------
+
+SPLINE_POLES = {
+    2: (np.sqrt(8.0) - 3.0,),
+    3: (np.sqrt(3.0) - 2.0,),
+    4: (np.sqrt(664.0 - np.sqrt(438976.0)) + np.sqrt(304.0) - 19.0,
+        np.sqrt(664.0 + np.sqrt(438976.0)) - np.sqrt(304.0) - 19.0),
+    5: (np.sqrt(67.5 - np.sqrt(4436.25)) + np.sqrt(26.25) - 6.5,
+        np.sqrt(67.5 + np.sqrt(4436.25)) - np.sqrt(26.25) - 6.5),
+}
+# boundary condition of the prefilter for each map_coordinates mode: 'nearest' runs on an input that
+# was padded by 12 edge samples and is then filtered with the half-sample-symmetric ("reflect")
+# initialisation; 'constant' and the legacy 'wrap' use the whole-sample-symmetric ("mirror") one.
+SPLINE_BOUNDARY = {'nearest': 'reflect', 'reflect': 'reflect', 'mirror': 'mirror', 'constant': 'mirror',
+                   'wrap': 'mirror'}
+SPLINE_NPAD = 12
+
+
+def spline_filter_axis0(a, order, boundary):
+    """B-spline coefficients of every column of `a` (lines along axis 0), in place semantics on a copy."""
+    c = np.array(a, dtype=np.float64)
+    n = c.shape[0]
+    if order < 2 or n < 2:
+        return c
+    poles = SPLINE_POLES[order]
+    gain = 1.0
+    for z in poles:
+        gain *= (1.0 - z) * (1.0 - 1.0 / z)
+    c *= gain
+    for z in poles:
+        src = c.copy()
+        if boundary == 'mirror':
+            zn1 = z ** (n - 1)
+            acc = src[0] + zn1 * src[n - 1]
+            z_i = z
+            for i in range(1, n - 1):
+                acc = acc + z_i * (src[i] + zn1 * src[n - 1 - i])
+                z_i *= z
+            c[0] = acc / (1.0 - zn1 * zn1)
+        else:
+            zn = z ** n
+            acc = src[0] + zn * src[n - 1]
+            z_i = z
+            for i in range(1, n):
+                acc = acc + z_i * (src[i] + zn * src[n - 1 - i])
+                z_i *= z
+            c[0] = acc * (z / (1.0 - zn * zn)) + src[0]
+        for i in range(1, n):
+            c[i] = c[i] + z * c[i - 1]
+        if boundary == 'mirror':
+            c[n - 1] = (z * c[n - 2] + c[n - 1]) * z / (z * z - 1.0)
+        else:
+            c[n - 1] = c[n - 1] * (z / (z - 1.0))
+        for i in range(n - 2, -1, -1):
+            c[i] = z * (c[i + 1] - c[i])
+    return c
+
+
+def spline_weights(order, x):
+    """First tap and the order+1 B-spline weights for coordinate x (a float)."""
+    if order % 2:
+        start = int(np.floor(x)) - order // 2
+    else:
+        start = int(np.floor(x + 0.5)) - order // 2
+    if order == 0:
+        return start, np.array([1.0])
+    if order == 1:
+        y = x - np.floor(x)
+        return start, np.array([1.0 - y, y])
+    if order == 2:
+        y = x - np.floor(x + 0.5)
+        w1 = 0.75 - y * y
+        t = 0.5 - y
+        w0 = 0.5 * t * t
+        return start, np.array([w0, w1, 1.0 - w0 - w1])
+    if order == 3:
+        y = x - np.floor(x)
+        z = 1.0 - y
+        w1 = (y * y * (y - 2.0) * 3.0 + 4.0) / 6.0
+        w2 = (z * z * (z - 2.0) * 3.0 + 4.0) / 6.0
+        w0 = z * z * z / 6.0
+        return start, np.array([w0, w1, w2, 1.0 - w0 - w1 - w2])
+    # orders 4, 5: the centred cardinal B-spline, beta^n(t) = 1/n! sum_k (-1)^k C(n+1,k) (t + (n+1)/2 - k)_+^n
+    from math import comb, factorial
+    w = np.zeros(order + 1)
+    for j in range(order + 1):
+        t = x - (start + j)
+        s = 0.0
+        for k in range(order + 2):
+            u = t + (order + 1) / 2.0 - k
+            if u > 0:
+                s += (-1) ** k * comb(order + 1, k) * u ** order
+        w[j] = s / factorial(order)
+    return start, w
+
+
+def _map_coordinate(c, n, mode):
+    """Coordinate extension of map_coordinates for modes without pre-padding; None = outside ('constant')."""
+    if mode == 'nearest':
+        return min(max(c, 0.0), n - 1.0)
+    if mode == 'constant':
+        return None if (c < 0 or c > n - 1) else c
+    if n <= 1:
+        return 0.0
+    if mode == 'mirror':
+        s2 = 2 * n - 2
+        if c < 0:
+            c = s2 * int(-c / s2) + c
+            return c + s2 if c <= 1 - n else -c
+        if c > n - 1:
+            c -= s2 * int(c / s2)
+            if c > n - 1:
+                c = s2 - c
+        return c
+    if mode == 'reflect':
+        s2 = 2 * n
+        if c < 0:
+            if c < -s2:
+                c = s2 * int(-c / s2) + c
+            return c + s2 if c < -n else -c - 1
+        if c > n - 1:
+            c -= s2 * int(c / s2)
+            if c >= n:
+                c = s2 - c - 1
+        return c
+    if mode == 'wrap':      # scipy's legacy 'wrap': period n - 1
+        sz = n - 1
+        if c < 0:
+            return c + sz * (int(-c / sz) + 1)
+        if c > n - 1:
+            return c - sz * int(c / sz)
+        return c
+    raise ValueError(f'unsupported mode {mode!r}')
+
+
+def _map_tap(i, n, boundary):
+    if 0 <= i < n:
+        return i
+    if boundary == 'mirror':
+        if n <= 1:
+            return 0
+        s2 = 2 * n - 2
+        i = abs(i) % s2
+        return s2 - i if i >= n else i
+    s2 = 2 * n
+    i = i % s2
+    return s2 - 1 - i if i >= n else i
+
+
+def spline_taps(coords, n, order, mode):
+    """Tap indices (into the prefiltered line of length n + 2*npad) and weights for every coordinate of a
+    1-D coordinate vector: (npad, idx[len, order+1] int64, w[len, order+1] float64).  A coordinate outside
+    the array in 'constant' mode gets zero weights (cval = 0, as util.py:334-343 never passes cval)."""
+    coords = np.asarray(coords, dtype=np.float64)
+    npad = SPLINE_NPAD if (mode == 'nearest' and order > 1) else 0
+    N = n + 2 * npad
+    idx = np.zeros((coords.size, order + 1), dtype=np.int64)
+    w = np.zeros((coords.size, order + 1), dtype=np.float64)
+    for k, c in enumerate(coords):
+        if npad:
+            # padded 'nearest': the coordinate is used as is, taps that leave the padded line are clamped
+            st, wk = spline_weights(order, float(c) + npad)
+            idx[k] = np.clip(st + np.arange(order + 1), 0, N - 1)
+            w[k] = wk
+            continue
+        cm = _map_coordinate(float(c), n, mode)
+        if cm is None:
+            continue
+        st, wk = spline_weights(order, cm)
+        idx[k] = [_map_tap(st + j, N, SPLINE_BOUNDARY[mode]) for j in range(order + 1)]
+        w[k] = wk
+    return npad, idx, w
+
+
+def map_coordinates_separable(img, y, x, order, mode):
+    """scipy.ndimage.map_coordinates(img, meshgrid(x, y)[::-1], order, mode) for real `img`."""
+    img = np.asarray(img, dtype=np.float64)
+    npad_y, iy, wy = spline_taps(y, img.shape[0], order, mode)
+    npad_x, ix, wx = spline_taps(x, img.shape[1], order, mode)
+    c = np.pad(img, npad_y, mode='edge') if npad_y else img
+    if order > 1:
+        b = SPLINE_BOUNDARY[mode]
+        c = spline_filter_axis0(c, order, b)                 # axis 0 first, then axis 1, as spline_filter does
+        c = spline_filter_axis0(c.T, order, b).T
+    out = np.zeros((len(y), len(x)))
+    for a in range(order + 1):                               # same tap order as the C loop: rows outer, columns inner
+        for bb in range(order + 1):
+            out = out + c[iy[:, a][:, None], ix[:, bb][None, :]] * wy[:, a][:, None] * wx[:, bb][None, :]
+    return out
+
+
+def rescale(img, scale, shape=None, mask=None, order=3, mode='nearest', unitary=True):
+    """lentil/util.py:261-347."""
+    img = np.asarray(img)
+    if mask is None:
+        mask = np.zeros_like(img).real
+        mask[img != 0] = 1
+    if shape is None:
+        shape = np.ceil((img.shape[0] * scale, img.shape[1] * scale)).astype(int)
+    elif np.isscalar(shape):
+        shape = np.ceil((shape * scale, shape * scale)).astype(int)
+    else:
+        shape = np.ceil((shape[0] * scale, shape[1] * scale)).astype(int)
+    x = (np.arange(shape[1], dtype=np.float64) - shape[1] / 2.) / scale + img.shape[1] / 2.
+    y = (np.arange(shape[0], dtype=np.float64) - shape[0] / 2.) / scale + img.shape[0] / 2.
+    mask = map_coordinates_separable(mask, y, x, 1, 'nearest')
+    mask[mask < np.finfo(mask.dtype).eps] = 0
+    if np.iscomplexobj(img):
+        out = np.zeros(shape, dtype=np.complex128)
+        out.real = map_coordinates_separable(img.real, y, x, order, mode)
+        out.imag = map_coordinates_separable(img.imag, y, x, order, mode)
+    else:
+        out = map_coordinates_separable(img, y, x, order, mode)
+    if unitary:
+        out *= np.sum(img) / np.sum(out)
+    out *= mask
+    return out
+
+
+def pixelate(img, oversample):
+    """lentil/detector.py:223-249."""
+    return rescale(pixel(img, oversample), 1 / oversample, order=3, mode='nearest', unitary=True)
+
+
+# --------------------------------------------------------------------------------------------
 # wavefront-error generator of BASELINE config 5 (next row): lentil/wfe.py:8-70
 # --------------------------------------------------------------------------------------------
 

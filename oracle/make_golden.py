@@ -295,6 +295,46 @@ def golden_detector():
     print("detector: oracle == reference bit-for-bit (rebin 2-D / cube, pixel MTF even / odd size)")
 
 
+def golden_rescale():
+    # lentil.rescale / lentil.detector.pixelate go through scipy.ndimage.map_coordinates (a dependency the
+    # reference does not vendor): the oracle restates that algorithm, so the pin is numerical (<= 1e-13 of the
+    # peak), not bit-for-bit; checked here with the scipy of the build container.
+    import scipy
+    rng = np.random.default_rng(78)
+    img = rng.random((60, 60))
+    img[:5] = 0
+    img[:, 50:] = 0
+    worst = 0.0
+    for scale in (1 / 2, 1 / 3, 0.37, 1.7):
+        for order in range(6):
+            for mode in ('nearest', 'constant', 'reflect', 'wrap'):
+                a = lentil.rescale(img, scale, order=order, mode=mode)
+                b = oc.rescale(img, scale, order=order, mode=mode)
+                worst = max(worst, float(np.max(np.abs(a - b)) / np.max(np.abs(a))))
+    assert worst <= 1e-13, worst
+    z = img + 1j * rng.random((60, 60))
+    psf = rng.random((96, 96)) ** 8
+    d = dict(img=img, z=z, psf=psf, scales=np.array([1 / 2, 1 / 3, 0.37, 1.7]))
+    cases = {}
+    for k, scale in enumerate(d["scales"]):
+        cases[f"default_{k}"] = lentil.rescale(img, scale)
+    for order in range(6):
+        cases[f"order{order}_third"] = lentil.rescale(img, 1 / 3, order=order)
+    for mode in ('constant', 'reflect', 'wrap'):
+        cases[f"mode_{mode}"] = lentil.rescale(img, 0.37, mode=mode)
+    cases["complex_half"] = lentil.rescale(z, 0.5)
+    cases["shape40_ones_nonunitary"] = lentil.rescale(img, 0.5, shape=40, mask=np.ones_like(img), unitary=False)
+    cases["pixelate3"] = lentil.detector.pixelate(psf, 3)
+    cases["pixelate4"] = lentil.detector.pixelate(psf, 4)
+    assert rel(oc.rescale(z, 0.5), cases["complex_half"]) <= 1e-13
+    assert rel(oc.rescale(img, 0.5, shape=40, mask=np.ones_like(img), unitary=False), cases["shape40_ones_nonunitary"]) <= 1e-13
+    assert rel(oc.pixelate(psf, 3), cases["pixelate3"]) <= 1e-13 and rel(oc.pixelate(psf, 4), cases["pixelate4"]) <= 1e-13
+    d.update(cases)
+    np.savez_compressed(os.path.join(GOLD, "rescale.npz"), **d)
+    print(f"rescale / pixelate: oracle == reference to {worst:.1e} of the peak over 96 (scale, order, mode) cases "
+          f"(scipy {scipy.__version__}); golden vectors written")
+
+
 def golden_dispersive_tilt():
     # the reference solves higher-order trace/dispersion polynomials with scipy leastsq / quad to
     # ~1e-8 relative (lentil/plane.py:1037,1050); these vectors pin the host mirror to that level
@@ -367,6 +407,7 @@ if __name__ == "__main__":
     golden_field()
     golden_propagate()
     golden_detector()
+    golden_rescale()
     golden_dispersive_tilt()
     golden_propagate_fft()
     golden_power_spectrum()

@@ -84,3 +84,51 @@ def test_power_spectrum_golden(golden):
         assert abs(rms - 30e-9) <= 1e-15
     with pytest.raises(ValueError):
         lentil.power_spectrum(np.ones((8, 9)), 1.0, 1e-9, 5, 3, seed=0)
+
+
+def test_rescale_golden(golden):
+    # lentil.rescale (lentil/util.py:261-347): every spline order, the four documented extension modes, complex
+    # input, explicit shape/mask, non-unitary — against vectors produced by the reference
+    from test_oracle_golden import rescale_golden_cases
+    d = golden("rescale")
+    for name, key, args, kw in rescale_golden_cases(d):
+        got = lentil.rescale(d[key], *args, **kw)
+        assert got.dtype == d[name].dtype, name
+        assert peak_err(got, d[name]) <= 1e-12, name
+    got = lentil.rescale(d["img"], 0.5, shape=40, mask=np.ones_like(d["img"]), unitary=False)
+    assert peak_err(got, d["shape40_ones_nonunitary"]) <= 1e-12
+
+
+def test_pixelate_golden_and_device_chain(golden):
+    d = golden("rescale")
+    for os_ in (3, 4):
+        assert peak_err(lentil.detector.pixelate(d["psf"], os_), d[f"pixelate{os_}"]) <= 1e-12
+    dev = lentil.device.to_dev(d["psf"])
+    out = lentil.detector.pixelate(dev, 3)
+    assert lentil.device.is_dev(out) and peak_err(lentil.device.to_host(out), d["pixelate3"]) <= 1e-12
+
+
+def test_rescale_matches_oracle_at_psf_size():
+    # a 1024^2 oversampled PSF brought to native sampling (BASELINE configs[1] detector), against the oracle
+    import lentil_oracle as oc
+    rng = np.random.default_rng(12)
+    img = rng.random((1024, 1024)) ** 6
+    img[:, :17] = 0
+    for scale, kw in ((0.5, {}), (1 / 3, {}), (0.25, dict(order=5)), (0.3, dict(mode="constant"))):
+        assert peak_err(lentil.rescale(img, scale, **kw), oc.rescale(img, scale, **kw)) <= 1e-12
+
+
+def test_rescale_small_and_degenerate_shapes():
+    import lentil_oracle as oc
+    rng = np.random.default_rng(13)
+    for shape in ((2, 2), (3, 7), (1, 5), (13, 2)):
+        img = rng.random(shape) + 0.1
+        for scale in (0.5, 1.0, 2.5):
+            for mode in ("nearest", "reflect", "constant"):
+                with np.errstate(all="ignore"):
+                    ref = oc.rescale(img, scale, mode=mode)
+                got = lentil.rescale(img, scale, mode=mode)
+                if not np.all(np.isfinite(ref)):        # a one-sample axis in 'constant' mode: sum(out) = 0, NaN in the reference too
+                    assert np.array_equal(np.isfinite(got), np.isfinite(ref))
+                    continue
+                assert peak_err(got, ref) <= 1e-12, (shape, scale, mode)

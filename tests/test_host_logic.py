@@ -294,3 +294,25 @@ def test_propagate_fft_refuses_tilt_before_touching_the_device():
     w = lentil.Wavefront(650e-9, tilt=[1e-6, 0])
     with pytest.raises(NotImplementedError):
         lentil.propagate_fft(w, pixelscale=5e-6, shape=(8, 8))
+
+
+def test_spline_tap_tables_match_the_oracle():
+    # host side of rescale (lentil/util.py:329-343): per-axis tap indices and B-spline weights for every order and
+    # extension mode, including coordinates outside the array
+    from lentil_b200.detector import _spline_taps
+    coords = np.array([-30.2, -13.5, -12.2, -3.2, -1.0, -0.4, 0, 0.49, 0.5, 1.0, 2.3, 7.5, 8.0, 8.3, 9.7, 13.1, 19.9, 50.0])
+    for n in (1, 2, 9, 40):
+        for order in range(6):
+            for mode in ("nearest", "constant", "reflect", "mirror", "wrap"):
+                npad, idx, w = _spline_taps(coords, n, order, mode)
+                rpad, ridx, rw = oc.spline_taps(coords, n, order, mode)
+                assert npad == rpad
+                live = np.abs(rw) > 0                      # taps with zero weight may point anywhere
+                assert np.array_equal(idx[live], ridx[live]), (n, order, mode)
+                assert np.max(np.abs(w - rw)) <= (1e-15 if order <= 3 else 5e-14), (n, order, mode)   # orders 4, 5: sum formula with cancellation
+                assert idx.min() >= 0 and idx.max() < n + 2 * npad
+
+
+def test_rescale_argument_errors():
+    with pytest.raises(RuntimeError):
+        lentil.rescale(np.ones((4, 4)), 0.5, order=7)

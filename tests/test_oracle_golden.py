@@ -152,3 +152,29 @@ def test_power_spectrum_golden(golden):
     for i in range(int(d["n"])):
         opd = oc.power_spectrum(d[f"c{i}_mask"], 1 / (2 * int(d[f"c{i}_radius"])), 30e-9, 5, 3, seed=int(d[f"c{i}_seed"]))
         assert np.array_equal(opd, d[f"c{i}_opd"])
+
+
+def rescale_golden_cases(d):
+    """(name, input key, args, kwargs) for every vector of tests/golden/rescale.npz."""
+    s = d["scales"]
+    cases = [(f"default_{k}", "img", (float(s[k]),), {}) for k in range(4)]
+    cases += [(f"order{o}_third", "img", (1 / 3,), dict(order=o)) for o in range(6)]
+    cases += [(f"mode_{m}", "img", (0.37,), dict(mode=m)) for m in ("constant", "reflect", "wrap")]
+    cases += [("complex_half", "z", (0.5,), {})]
+    return cases
+
+
+def test_rescale_golden(golden):
+    # lentil/util.py:261-347 through scipy.ndimage.map_coordinates: numerical pin (1e-13 of the peak)
+    d = golden("rescale")
+    for name, key, args, kw in rescale_golden_cases(d):
+        got = oc.rescale(d[key], *args, **kw)
+        assert got.shape == d[name].shape, name
+        assert np.max(np.abs(got - d[name])) <= 1e-13 * np.max(np.abs(d[name])), name
+    got = oc.rescale(d["img"], 0.5, shape=40, mask=np.ones_like(d["img"]), unitary=False)
+    assert np.max(np.abs(got - d["shape40_ones_nonunitary"])) <= 1e-13 * np.max(d["shape40_ones_nonunitary"])
+    for os_ in (3, 4):
+        ref = d[f"pixelate{os_}"]
+        got = oc.pixelate(d["psf"], os_)
+        assert got.shape == ref.shape == (96 // os_, 96 // os_)
+        assert np.max(np.abs(got - ref)) <= 1e-13 * ref.max()
