@@ -281,7 +281,7 @@ struct FoldSplit {
     const unsigned char *mask;       // this segment's mask plane, or NULL
     long long pld;                   // pupil row stride (n_c)
     int pr0, pc0;
-    double wavelength;
+    double wavelength;               // 1 / lambda
 };
 
 // the phase is reduced in fp64 (in cycles) before the sine/cosine, the phasor is then rounded to complex64
@@ -290,10 +290,14 @@ __device__ __forceinline__ float2 pupil_phasor_c64(const FoldSplit &d, int i, in
     double a = d.amp[pix];
     if (d.mask != nullptr && d.mask[pix] == 0) a = 0.0;
     if (a == 0.0) return make_float2(0.f, 0.f);
-    const double tcyc = d.opd[pix] / d.wavelength;
-    double sn, cs;
-    sincospi(2.0 * (tcyc - rint(tcyc)), &sn, &cs);
-    return make_float2((float)(a * cs), (float)(a * sn));
+    // the phase is formed and reduced to (-1/2, 1/2] cycles in fp64 (opd / lambda is ~1e1 .. 1e3 cycles), the sine and
+    // cosine of the reduced phase are then fp32: the phasor is rounded to complex64 anyway, and the fp64 sincospi
+    // made this kernel FP64-issue bound
+    const double tcyc = d.opd[pix] * d.wavelength;          // wavelength holds 1 / lambda here (set by the launcher)
+    float sn, cs;
+    sincospif(2.0f * (float)(tcyc - rint(tcyc)), &sn, &cs);
+    const float af = (float)a;
+    return make_float2(af * cs, af * sn);
 }
 
 __global__ void __launch_bounds__(256)
@@ -779,7 +783,7 @@ int launch_mft_c64(const lfd_mft_desc *descs, int count, void *workspace, size_t
         f.kmax = kmax_dev; f.ntile = g.slots1 / TN; f.pad_ = 0;
         if (src) {
             f.amp = src[i].amp; f.opd = src[i].opd; f.mask = src[i].mask;
-            f.pld = src[i].n_c; f.pr0 = src[i].r0; f.pc0 = src[i].c0; f.wavelength = src[i].wavelength;
+            f.pld = src[i].n_c; f.pr0 = src[i].r0; f.pc0 = src[i].c0; f.wavelength = 1.0 / src[i].wavelength;
         }
         if (g.slots1 / TN > max_fs_x) max_fs_x = g.slots1 / TN;
         if (g.Kpad1 / 32 > max_fs_y) max_fs_y = g.Kpad1 / 32;

@@ -44,9 +44,17 @@ pupil_prep_kernel(const double *__restrict__ amp, const double *__restrict__ opd
         for (int l = 0; l < P.nlam; ++l) {
             double tcyc = o / P.lam[l];           // phase in cycles
             double r = tcyc - rint(tcyc);          // exact: |r| <= 0.5
-            double s, c;
-            sincospi(2.0 * r, &s, &c);
-            dst[(long long)l * lam_stride] = make_cplx<CT>(a * c, a * s);
+            if constexpr (sizeof(CT) == sizeof(float2)) {
+                // complex64 output: fp32 sine/cosine of the fp64-reduced phase (as in the fused fold of mft_c64.cu)
+                float s, c;
+                sincospif(2.0f * (float)r, &s, &c);
+                const float af = (float)a;
+                dst[(long long)l * lam_stride] = make_float2(af * c, af * s);
+            } else {
+                double s, c;
+                sincospi(2.0 * r, &s, &c);
+                dst[(long long)l * lam_stride] = make_cplx<CT>(a * c, a * s);
+            }
         }
     }
 }
