@@ -1,6 +1,6 @@
 """Turn gpurun_out ncu artefacts into the tracked summaries under profiles/.
 
-    python scripts/summarize_ncu.py <launches.csv> <prof.ncu-rep> <tag>
+    python scripts/summarize_ncu.py <launches.csv> <prof.ncu-rep> <tag> [planes per profiled launch, default 8]
 
 writes profiles/<tag>_launches.json (per-kernel time shares of the bench command) and
 profiles/<tag>_mft_ncu.json (+ profiles/mft_ncu_summary.json, which bench.py reads for
@@ -14,6 +14,7 @@ import sys
 from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NPLANES = int(sys.argv[4]) if len(sys.argv) > 4 else 8      # planes per launch of the profiled target (scripts/ncu_target.py N)
 
 
 def launches(path):
@@ -74,9 +75,9 @@ if __name__ == "__main__":
     mft = [d for d in F if "mft" in d["kernel"]]
     if mft:
         tr = sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in mft) / len(mft)
-        json.dump({"dram_bytes_per_launch": tr, "planes_per_profiled_launch": 8,
-                   "dram_bytes_per_plane_stage": tr / 8, "source": f"profiles/{tag}_mft_ncu.json",
-                   "note": "ncu --set full on scripts/ncu_target.py (8 planes 1001^2->1024^2 per launch)",
+        json.dump({"dram_bytes_per_launch": tr, "planes_per_profiled_launch": NPLANES,
+                   "dram_bytes_per_plane_stage": tr / NPLANES, "source": f"profiles/{tag}_mft_ncu.json",
+                   "note": f"ncu --set full on scripts/ncu_target.py ({NPLANES} planes 1001^2->1024^2 per launch)",
                    "tensor_pipe_active_pct": sum(d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0) for d in mft) / len(mft)},
                   open(os.path.join(ROOT, "profiles", "mft_ncu_summary.json"), "w"), indent=1)
     for k in L["kernels"]:
