@@ -13,7 +13,7 @@ there is no CPU fallback.
 __version__ = '0.1.0'
 
 from .ptype import ptype, none, pupil, image, tilt, transform  # noqa: F401
-from . import extent, helper, field, fourier, plane, propagate, wavefront, device, detector, wfe  # noqa: F401
+from . import extent, helper, field, fourier, plane, propagate, wavefront, device, detector, wfe, patch  # noqa: F401
 from .field import Field  # noqa: F401
 from .plane import Plane, Pupil, Image, Tilt, DispersiveTilt, Grism  # noqa: F401
 from .wavefront import Wavefront  # noqa: F401

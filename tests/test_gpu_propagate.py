@@ -417,3 +417,27 @@ def test_propagate_fft_equals_dft_at_the_fft_sampling():
     assert wf.field.shape == wd.field.shape == (48, 48)
     assert peak_err(wf.field, wd.field) <= 1e-9
     assert peak_err(wf.intensity, wd.intensity) <= 1e-9
+
+
+def test_fourier_level_patch_reroutes_a_numpy_propagation(golden):
+    # rebinding <module>.dft2 sends a host-side propagate_dft (here the oracle's restatement of
+    # lentil/propagate.py:147-242, which like the reference resolves dft2 through its module at call time) through K2a
+    import lentil_oracle as oc
+    from lentil_b200 import patch
+    d = golden("propagate")
+    dx, z, du = float(d["A_dx"]), float(d["A_z"]), float(d["A_du"])
+    args = (d["A_amp"], d["A_opd"], None, d["A_wls"], d["A_wts"], (dx, dx), z, du, tuple(d["A_shape"]), None, int(d["A_oversample"]))
+    kw = dict(wf_tilt=list(d["A_tilt"]))
+    ref = oc.psf(*args, **kw)
+    import types
+    shim = types.SimpleNamespace(fourier=oc)            # the oracle module plays lentil.fourier: it owns dft2 / idft2
+    n0 = lentil.device.launch_count()
+    patch.enable(shim)
+    try:
+        assert oc.dft2 is lentil.fourier.dft2
+        got = oc.psf(*args, **kw)
+    finally:
+        patch.disable(shim)
+    assert oc.dft2 is not lentil.fourier.dft2
+    assert lentil.device.launch_count() - n0 >= len(d["A_wls"])      # one K2a launch group per wavelength
+    assert peak_err(got, ref) <= TOL64 and peak_err(got, d["A_img"]) <= TOL64

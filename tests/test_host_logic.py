@@ -316,3 +316,25 @@ def test_spline_tap_tables_match_the_oracle():
 def test_rescale_argument_errors():
     with pytest.raises(RuntimeError):
         lentil.rescale(np.ones((4, 4)), 0.5, order=7)
+
+
+def test_patch_rebinds_and_restores_the_reference_entry_points():
+    # lentil resolves dft2 / propagate_dft through module attributes at call time
+    import types
+    from lentil_b200 import patch, fourier, propagate, detector
+    ref = types.SimpleNamespace(
+        fourier=types.SimpleNamespace(dft2="ref_dft2", idft2="ref_idft2"),
+        propagate=types.SimpleNamespace(propagate_dft="ref_prop"), propagate_dft="ref_prop",
+        util=types.SimpleNamespace(rebin="ref_rebin", rescale="ref_rescale"), rebin="ref_rebin", rescale="ref_rescale",
+        detector=types.SimpleNamespace(pixel="ref_pixel"))              # no pixelate: must be skipped, not created
+    patch.enable(ref)
+    assert ref.fourier.dft2 is fourier.dft2 and ref.fourier.idft2 is fourier.idft2 and ref.propagate_dft == "ref_prop"
+    patch.enable(ref, level='path')
+    assert ref.propagate.propagate_dft is propagate.propagate_dft and ref.propagate_dft is propagate.propagate_dft
+    assert ref.util.rescale is detector.rescale and ref.rebin is detector.rebin and ref.detector.pixel is detector.pixel
+    assert not hasattr(ref.detector, "pixelate")
+    patch.disable(ref)
+    assert ref.fourier.dft2 == "ref_dft2" and ref.propagate.propagate_dft == "ref_prop" and ref.util.rescale == "ref_rescale"
+    assert ref.detector.pixel == "ref_pixel" and ref.rebin == "ref_rebin"
+    with pytest.raises(ValueError):
+        patch.enable(ref, level='everything')
