@@ -64,6 +64,9 @@ constexpr int ACC_COLS = 4 * NR;               // TMEM columns of the accumulato
 constexpr int A_STAGE_COLS = 32;               // 4 planes x 8 K
 static_assert(ACC_COLS + NA * A_STAGE_COLS <= 512, "TMEM budget");
 static_assert(NB == 12 && NA == 4, "the issuer's loop is unrolled over lcm(NA, NB) = 12 blocks, and 12 / NA must be odd");
+#ifndef LFD_EB_QUARTER
+#define LFD_EB_QUARTER 1      // lane quarter whose generator warps hand retired data slots back to the producer
+#endif
 #ifndef LFD_PROD_NS
 #define LFD_PROD_NS 100
 #endif
@@ -518,11 +521,20 @@ mft_c64_kernel(const CStage *__restrict__ descs) {
         for (int jb = set; jb < nblk; jb += NSETS) {
             const int s = jb % NA;
             TRACE_IF(lane == 0 && warp == 3, 5, jb)
+            TRACE_IF(lane == 0 && warp == 1, 10, jb)          // warp 1's timeline goes to the set-1 rows (free at even jb)
             TT_BEGIN
             // twiddles of this row for the 8 K of the block: columns cos_hi[8] | cos_lo[8] | sin_hi[8] | sin_lo[8]
             float v[32];
+#ifdef LFD_X_NOCOMPUTE      /* timing experiment (wrong results): constant twiddles, no arithmetic in the K loop */
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = S[j & 7].x;
+#else
             {
+#ifdef LFD_X_NOFP64         /* timing experiment (wrong results): no FP64 instruction in the K loop */
+                const float wc = S[1].x + (float)jb, ws = S[1].y;
+#else
                 const float wc = (float)Wc, ws = (float)Ws;
+#endif
                 v[0] = tf32_hi(wc); v[8] = wc - v[0]; v[16] = tf32_hi(ws); v[24] = ws - v[16];     // S[0] = 1
 #pragma unroll
                 for (int j = 1; j < KB; ++j) {
@@ -530,23 +542,36 @@ mft_c64_kernel(const CStage *__restrict__ descs) {
                     v[j] = tf32_hi(c); v[8 + j] = c - v[j];
                     v[16 + j] = tf32_hi(sn); v[24 + j] = sn - v[16 + j];
                 }
+#ifndef LFD_X_NOFP64
                 const double nc = Wc * Rc - Ws * Rs, ns = Wc * Rs + Ws * Rc;
                 Wc = nc; Ws = ns;
+#endif
             }
+#endif
             TT_ADD(tt_b)
+            TRACE_IF(lane == 0 && warp == 1, 11, jb)
             // the twiddle stage must have been consumed before it is overwritten
             if (jb >= NA) {
                 mbar_wait(&emptyA_bar[s], ((jb / NA) - 1) & 1);
                 TRACE_IF(lane == 0 && warp == 3, 2, jb)
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 // block jb - NA has retired: hand its data slot back to the producer
-                if (quarter == 1 && lane == 0) mbar_arrive(&emptyB_bar[(jb - NA) % NB]);
+                if (quarter == LFD_EB_QUARTER && lane == 0) mbar_arrive(&emptyB_bar[(jb - NA) % NB]);
             }
             TRACE_IF(lane == 0 && (warp == 3 || warp == 4), warp, jb)
+            TRACE_IF(lane == 0 && warp == 1, 12, jb)
             TT_ADD(tt_a)
+#ifdef LFD_X_NOST           /* timing experiment (wrong results): the twiddles are computed but not written to TMEM */
+            { float acc = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc += v[j];
+              if (acc == 123.456f) tmem_st32(tw + s * A_STAGE_COLS, v); }
+#else
             tmem_st32(tw + s * A_STAGE_COLS, v);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#endif
             TRACE_IF(lane == 0 && (warp == 3 || warp == 4), warp + 11, jb)
+            TRACE_IF(lane == 0 && warp == 1, 13, jb)
             asm volatile("tcgen05.fence::before_thread_sync;");
             asm volatile("bar.arrive %0, %1;" ::"r"(1 + s), "r"(32 + 128) : "memory");
             TRACE_IF(lane == 0, 5 + warp, jb)

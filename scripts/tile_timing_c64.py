@@ -56,6 +56,8 @@ if os.environ.get("LFD_TT_TRACE"):
     t0 = tr[0, 0]
     print("jb : issue start | issue end | waits done || arrival of generator warps on fullA(jb) (cycles since first issue)")
     for j in range(14, 44):
-        arr = [int(tr[6 + w, j] - t0) for w in range(8) if tr[6 + w, j] > 0]
+        arr = [int(tr[6 + w, j] - t0) for w in (range(4) if j % 2 == 0 else range(4, 8))]
         extra = "  w3: loop-top %d barrier-passed %d computed %d st-done %d arrive %d | w4: computed %d st-done %d arrive %d" % tuple(int(tr[e, j] - t0) for e in (5, 2, 3, 14, 8, 4, 15, 9)) if j % 2 == 0 else ""
+        if j % 2 == 0:
+            extra += "  w1: loop-top %d computed %d wait+fence done %d st-done %d arrive %d" % tuple(int(tr[e, j] - t0) for e in (10, 11, 12, 13, 6))
         print(f"{j:3d}: {int(tr[0, j] - t0):8d} | {int(tr[1, j] - t0):8d} | {int(tr[2, j] - t0):8d} || " + " ".join(f"{a:7d}" for a in arr) + extra)
