@@ -60,12 +60,16 @@ typedef struct lfd_mft_desc {
     int32_t     inverse;            /* 0: dft2, 1: idft2 semantics                     */
 } lfd_mft_desc;
 
-/* Two executions of the same transform (results agree to rounding):
+/* Three executions of the same transform (results agree to rounding):
  *   LFD_MFT_DIRECT : complex twiddle x complex data, 4 real DMMAs per complex 8x8x4 block
  *   LFD_MFT_FOLDED : even/odd folding of both axes -> real twiddles, 4x fewer DMMAs (default)
+ *   LFD_MFT_CZT    : chirp-z (Bluestein) execution on the FP64 pipe: per row FFT_L -> x FFT(chirp) -> IFFT_L in shared
+ *                    memory, ~8x fewer flops than the folded form; planes whose FFT length would exceed 4096
+ *                    (n_in + n_out - 1 > 4096 on an axis) are run by the folded execution instead
  * Process-wide switch; affects lfd_mft_workspace_bytes and the lfd_mft_* launches that follow. */
 #define LFD_MFT_DIRECT 0
 #define LFD_MFT_FOLDED 1
+#define LFD_MFT_CZT    2
 int lfd_set_mft_variant(int variant);
 int lfd_get_mft_variant(void);
 

@@ -6,7 +6,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["capi.cu", "mft_c128.cu", "mft_folded.cu", "mft_c64.cu", "pupil_prep.cu", "accum.cu", "fit_tilt.cu", "detector_ops.cu", "rescale.cu"]
+SOURCES = ["capi.cu", "mft_c128.cu", "mft_folded.cu", "mft_czt.cu", "mft_c64.cu", "pupil_prep.cu", "accum.cu", "fit_tilt.cu", "detector_ops.cu", "rescale.cu"]
 HEADERS = ["lfd_common.cuh", os.path.join(ROOT, "include", "lentil_b200.h")]
 LIB = os.path.join(os.path.dirname(HERE), "liblentil_b200.so")
 

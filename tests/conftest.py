@@ -54,12 +54,12 @@ def unpack_fields(d, prefix):
 TOL64 = 1e-10
 
 
-@pytest.fixture(params=["folded", "direct"])
+@pytest.fixture(params=["folded", "direct", "czt"])
 def mft_variant(request):
     """Run a test under both executions of K2a (LFD_MFT_FOLDED is the default, LFD_MFT_DIRECT the
     plain complex x complex form); restores the default afterwards."""
     from lentil_b200 import _lib
     L = _lib.lib()
-    L.lfd_set_mft_variant(1 if request.param == "folded" else 0)
+    L.lfd_set_mft_variant({"direct": 0, "folded": 1, "czt": 2}[request.param])
     yield request.param
     L.lfd_set_mft_variant(1)
