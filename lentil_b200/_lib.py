@@ -130,6 +130,10 @@ def lib():
         for which, struct in enumerate((MftDesc, Segment, Window)):
             if handle.lfd_struct_size(which) != C.sizeof(struct):
                 raise LfdError(f"ABI struct layout mismatch for {struct.__name__}")
+        v = os.environ.get("LFD_MFT_VARIANT")          # direct | folded | czt: process-wide execution of K2a (default: the library's)
+        if v:
+            if handle.lfd_set_mft_variant({"direct": 0, "folded": 1, "czt": 2}[v.lower()]) != 0:
+                raise LfdError(f"LFD_MFT_VARIANT={v!r} rejected")
         _lib = handle
     return _lib
 

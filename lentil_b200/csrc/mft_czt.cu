@@ -81,15 +81,24 @@ template <int S> __device__ __forceinline__ void dft8(double2 (&v)[8]) {
     v[1] = b0; v[3] = b1; v[5] = b2; v[7] = b3;
 }
 
-// One Stockham pass of radix R over a length-L sequence for butterfly j: reads in[j + r L/R], multiplies by the pass
-// twiddles exp(-+ 2 pi i r k / (Ns R)), k = j mod Ns, takes the R-point DFT and writes out[(j - k) R + k + r Ns].
-template <int R, int S, int LOG2L>
-__device__ __forceinline__ void pass(const double2 *in, double2 *out, int j, int Ns) {
+// Element sources / sinks of a pass: shared memory (padded layout), or the caller's functor (global memory).
+struct SmemIn  { const double2 *p; __device__ __forceinline__ double2 operator()(int i) const { return p[P(i)]; } };
+struct SmemOut { double2 *p; __device__ __forceinline__ void operator()(int i, double2 v) const { p[P(i)] = v; } };
+// last pass of the forward transform: the spectrum is multiplied by H on its way to shared memory
+struct SmemTimesH {
+    double2 *p; const double2 *__restrict__ H;
+    __device__ __forceinline__ void operator()(int i, double2 v) const { p[P(i)] = cmul(v, H[i]); }
+};
+
+// One Stockham pass of radix R over a length-L sequence for butterfly j: reads in(j + r L/R), multiplies by the pass
+// twiddles exp(-+ 2 pi i r k / (Ns R)), k = j mod Ns, takes the R-point DFT and writes out((j - k) R + k + r Ns).
+template <int R, int S, int LOG2L, class In, class Out>
+__device__ __forceinline__ void pass(const In &in, const Out &out, int j, int Ns) {
     constexpr int L = 1 << LOG2L;
     const int k = j & (Ns - 1);
     double2 v[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = in[P(j + r * (L / R))];
+    for (int r = 0; r < R; ++r) v[r] = in(j + r * (L / R));
     if (Ns > 1) {
         double2 w1 = g_roots[k * (L / (Ns * R)) * (ROOTS / L)];
         if (S < 0) w1.y = -w1.y;
@@ -102,33 +111,46 @@ __device__ __forceinline__ void pass(const double2 *in, double2 *out, int j, int
     else dft2p<S>(v[0], v[1]);
     const int j0 = (j - k) * R + k;
 #pragma unroll
-    for (int r = 0; r < R; ++r) out[P(j0 + r * Ns)] = v[r];
+    for (int r = 0; r < R; ++r) out(j0 + r * Ns, v[r]);
 }
 
-// FFT of the L elements in `a` (padded layout) with L / 8 threads; `b` is the second buffer.  Returns the buffer that
-// holds the result (natural order).  Ends with a __syncthreads().
-template <int S, int LOG2L>
-__device__ __forceinline__ double2 *fft(double2 *a, double2 *b, int t) {
-    constexpr int L = 1 << LOG2L, T = L / 8, N8 = LOG2L / 3, REM = LOG2L % 3;
-    int Ns = 1;
+// all butterflies of one pass that thread t owns (L / 8 threads: one radix-8, two radix-4 or four radix-2 butterflies)
+template <int R, int S, int LOG2L, class In, class Out>
+__device__ __forceinline__ void pass_all(const In &in, const Out &out, int t, int Ns) {
+    constexpr int T = (1 << LOG2L) / 8;
 #pragma unroll
-    for (int p = 0; p < N8; ++p) {
-        pass<8, S, LOG2L>(a, b, t, Ns);
+    for (int q = 0; q < 8 / R; ++q) pass<R, S, LOG2L>(in, out, t + q * T, Ns);
+}
+
+// FFT of L elements with L / 8 threads.  The first pass reads through `first` (shared memory or a functor that loads
+// from global memory: the input never makes a separate trip through shared memory), the last pass writes through `last`
+// (shared memory, shared memory x H, or global memory); the passes in between ping-pong between the padded buffers a
+// and b, starting by WRITING a.  Every pass is followed by a __syncthreads().  Returns the buffer the last pass would
+// have written had it gone to shared memory (what `last` should point at when it is a shared-memory sink).
+template <int LOG2L> __device__ __forceinline__ double2 *fft_result_buffer(double2 *a, double2 *b) {
+    constexpr int NPASS = LOG2L / 3 + (LOG2L % 3 ? 1 : 0);
+    return (NPASS & 1) ? a : b;
+}
+template <int S, int LOG2L, class In, class Out>
+__device__ __forceinline__ void fft(double2 *a, double2 *b, int t, const In &first, const Out &last) {
+    constexpr int N8 = LOG2L / 3, REM = LOG2L % 3, NPASS = N8 + (REM ? 1 : 0);
+    constexpr int RLAST = REM == 0 ? 8 : (REM == 2 ? 4 : 2);
+    static_assert(NPASS >= 2, "at least two passes");
+    int Ns = 1;
+    // first pass: radix 8 from `first` into a
+    pass_all<8, S, LOG2L>(first, SmemOut{a}, t, Ns);
+    __syncthreads();
+    Ns *= 8;
+    double2 *src = a, *dst = b;
+#pragma unroll
+    for (int p = 1; p < NPASS - 1; ++p) {
+        pass_all<8, S, LOG2L>(SmemIn{src}, SmemOut{dst}, t, Ns);
         __syncthreads();
-        double2 *x = a; a = b; b = x;
+        double2 *x = src; src = dst; dst = x;
         Ns *= 8;
     }
-    if constexpr (REM == 2) {
-        pass<4, S, LOG2L>(a, b, t, Ns); pass<4, S, LOG2L>(a, b, t + T, Ns);
-        __syncthreads();
-        double2 *x = a; a = b; b = x;
-    } else if constexpr (REM == 1) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) pass<2, S, LOG2L>(a, b, t + q * T, Ns);
-        __syncthreads();
-        double2 *x = a; a = b; b = x;
-    }
-    return a;
+    pass_all<RLAST, S, LOG2L>(SmemIn{src}, last, t, Ns);
+    __syncthreads();
 }
 
 __device__ __forceinline__ double2 pupil_phasor(const Plane &d, int i, int c) {
@@ -169,20 +191,18 @@ czt_tables_kernel(const Plane *__restrict__ descs) {
     }
     double2 *a = sm, *b = sm + (L + L / 8);
     const double dd = y0 - x0;                       // D = (u - i) + (y0 - x0)
-    for (int q = t; q < L; q += T) {
-        // circular position q holds the lag p = u - i: p = q for q < nout, p = q - L for the negative lags
+    const double sg = d.sgn;
+    // circular position q holds the lag p = u - i: p = q for q < nout, p = q - L for the negative lags
+    auto chirp = [=](int q) -> double2 {
         const int p = q < nout ? q : q - L;
-        double2 hv = make_double2(0.0, 0.0);
-        if (p > -nin && p < nout) {
-            const double D = (double)p + dd;
-            cis_cycles(alpha, D, 0.5 * D, -d.sgn, c, s);
-            hv = make_double2(c, s);
-        }
-        a[P(q)] = hv;
-    }
-    __syncthreads();
-    const double2 *r = fft<1, LOG2L>(a, b, t);
-    for (int q = t; q < L; q += T) H[q] = r[P(q)];
+        if (p <= -nin || p >= nout) return make_double2(0.0, 0.0);
+        const double D = (double)p + dd;
+        double cc, ss;
+        cis_cycles(alpha, D, 0.5 * D, -sg, cc, ss);
+        return make_double2(cc, ss);
+    };
+    auto to_H = [=](int q, double2 v) { H[q] = v; };
+    fft<1, LOG2L>(a, b, t, chirp, to_H);
 }
 
 // ---- one stage: every row of every plane whose FFT length is L ----------------------------------------------
@@ -205,36 +225,34 @@ czt_stage_kernel(const Plane *__restrict__ descs, int count, int max_rows) {
         const double2 *__restrict__ pre = STAGE_A ? d.preA : d.preB;
         const double2 *__restrict__ post = STAGE_A ? d.postA : d.postB;
         const double2 *__restrict__ H = STAGE_A ? d.HA : d.HB;
-#pragma unroll
-        for (int i = t; i < L; i += T) {
-            double2 x = make_double2(0.0, 0.0);
-            if (i < nin) {
-                if (STAGE_A) x = d.amp != nullptr ? pupil_phasor(d, row, i) : d.f[(long long)row * d.ldf + i];
-                else x = d.Gt[(long long)row * d.mpad + i];
-                x = cmul(x, pre[i]);
-            }
-            a[P(i)] = x;
-        }
-        __syncthreads();
-        double2 *r = fft<1, LOG2L>(a, b, t);
-        double2 *o = (r == a) ? b : a;
-#pragma unroll
-        for (int i = t; i < L; i += T) r[P(i)] = cmul(r[P(i)], H[i]);
-        __syncthreads();
-        const double2 *y = fft<-1, LOG2L>(r, o, t);
+        const Plane *dp = &d;
+        // first forward pass reads the row straight from global memory (x pre-chirp; zero beyond the input length)
+        auto load = [=](int i) -> double2 {
+            if (i >= nin) return make_double2(0.0, 0.0);
+            double2 x;
+            if (STAGE_A) x = dp->amp != nullptr ? pupil_phasor(*dp, row, i) : dp->f[(long long)row * dp->ldf + i];
+            else x = dp->Gt[(long long)row * dp->mpad + i];
+            return cmul(x, pre[i]);
+        };
+        double2 *spec = fft_result_buffer<LOG2L>(a, b);               // where the spectrum (x H) lands
+        double2 *other = (spec == a) ? b : a;
+        fft<1, LOG2L>(a, b, t, load, SmemTimesH{spec, H});
+        // inverse transform: reads the spectrum, ping-pongs starting with `other`, last pass goes to global memory
         if (STAGE_A) {
-            for (int i = t; i < nout; i += T) d.Gt[(long long)i * d.mpad + row] = cmul(y[P(i)], post[i]);
-        } else if (d.intensity) {
-            double *out = (double *)d.out;
-            for (int i = t; i < nout; i += T) {
-                const double2 v = cmul(y[P(i)], post[i]);
-                out[(long long)i * d.ldo + row] = v.x * v.x + v.y * v.y;
-            }
+            double2 *Gt = dp->Gt; const long long mpad = dp->mpad;
+            auto store = [=](int i, double2 v) { if (i < nout) Gt[(long long)i * mpad + row] = cmul(v, post[i]); };
+            fft<-1, LOG2L>(other, spec, t, SmemIn{spec}, store);
+        } else if (dp->intensity) {
+            double *out = (double *)dp->out; const long long ldo = dp->ldo;
+            auto store = [=](int i, double2 v) {
+                if (i < nout) { const double2 z = cmul(v, post[i]); out[(long long)i * ldo + row] = z.x * z.x + z.y * z.y; }
+            };
+            fft<-1, LOG2L>(other, spec, t, SmemIn{spec}, store);
         } else {
-            double2 *out = (double2 *)d.out;
-            for (int i = t; i < nout; i += T) out[(long long)i * d.ldo + row] = cmul(y[P(i)], post[i]);
+            double2 *out = (double2 *)dp->out; const long long ldo = dp->ldo;
+            auto store = [=](int i, double2 v) { if (i < nout) out[(long long)i * ldo + row] = cmul(v, post[i]); };
+            fft<-1, LOG2L>(other, spec, t, SmemIn{spec}, store);
         }
-        __syncthreads();
     }
 }
 
