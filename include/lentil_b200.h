@@ -70,8 +70,12 @@ typedef struct lfd_mft_desc {
 #define LFD_MFT_DIRECT 0
 #define LFD_MFT_FOLDED 1
 #define LFD_MFT_CZT    2
+#define LFD_MFT_AUTO   3   /* default: chirp-z when every plane of the batch has an FFT length of 2048 or 4096 on one
+                            * of its axes (where it is measured faster than the folded form), else folded */
 int lfd_set_mft_variant(int variant);
 int lfd_get_mft_variant(void);
+/* which execution (LFD_MFT_DIRECT / FOLDED / CZT) a batch runs under the current setting */
+int lfd_mft_execution(const lfd_mft_desc *descs_host, int count);
 
 /* bytes of device workspace lfd_mft_c128_batched needs for `count` planes whose largest
  * intermediate is max over planes of (n * M) complex elements */

@@ -64,6 +64,7 @@ SIGNATURES = {
     "lfd_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
     "lfd_set_mft_variant": (C.c_int, [C.c_int]),
     "lfd_get_mft_variant": (C.c_int, []),
+    "lfd_mft_execution": (C.c_int, [C.POINTER(MftDesc), C.c_int]),
     "lfd_mft_workspace_bytes": (C.c_size_t, [C.POINTER(MftDesc), C.c_int]),
     "lfd_mft_c128_batched": (C.c_int, [C.POINTER(MftDesc), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "lfd_mft_c128": (C.c_int, [C.POINTER(MftDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -130,9 +131,9 @@ def lib():
         for which, struct in enumerate((MftDesc, Segment, Window)):
             if handle.lfd_struct_size(which) != C.sizeof(struct):
                 raise LfdError(f"ABI struct layout mismatch for {struct.__name__}")
-        v = os.environ.get("LFD_MFT_VARIANT")          # direct | folded | czt: process-wide execution of K2a (default: the library's)
+        v = os.environ.get("LFD_MFT_VARIANT")          # direct | folded | czt | auto: process-wide execution of K2a (default: the library's)
         if v:
-            if handle.lfd_set_mft_variant({"direct": 0, "folded": 1, "czt": 2}[v.lower()]) != 0:
+            if handle.lfd_set_mft_variant({"direct": 0, "folded": 1, "czt": 2, "auto": 3}[v.lower()]) != 0:
                 raise LfdError(f"LFD_MFT_VARIANT={v!r} rejected")
         _lib = handle
     return _lib

@@ -187,26 +187,38 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
                       cudaStream_t stream, const lfd_pupil_src *src, int intensity_out);
 
 bool czt_supported(const lfd_mft_desc *descs, int count);
+bool czt_preferred(const lfd_mft_desc *descs, int count);
 size_t czt_workspace_bytes(const lfd_mft_desc *descs, int count);
 int launch_mft_czt(const lfd_mft_desc *descs, int count, void *workspace, size_t workspace_bytes, cudaStream_t stream,
                    const lfd_pupil_src *src, int intensity_out);
 
-static std::atomic<int> g_variant{LFD_MFT_FOLDED};
+static std::atomic<int> g_variant{LFD_MFT_AUTO};
+
+// the execution a batch runs under the current process-wide setting
+int mft_resolve_execution(const lfd_mft_desc *descs, int count) {
+    const int v = g_variant.load();
+    if (v == LFD_MFT_CZT) return czt_supported(descs, count) ? LFD_MFT_CZT : LFD_MFT_FOLDED;
+    if (v == LFD_MFT_AUTO) return czt_preferred(descs, count) ? LFD_MFT_CZT : LFD_MFT_FOLDED;
+    return v;
+}
 
 }  // namespace lfd
 
 using namespace lfd;
 
 extern "C" int lfd_set_mft_variant(int variant) {
-    LFD_REQUIRE(variant == LFD_MFT_DIRECT || variant == LFD_MFT_FOLDED || variant == LFD_MFT_CZT, "unknown MFT variant %d", variant);
+    LFD_REQUIRE(variant >= LFD_MFT_DIRECT && variant <= LFD_MFT_AUTO, "unknown MFT variant %d", variant);
     g_variant.store(variant);
     return 0;
 }
 extern "C" int lfd_get_mft_variant(void) { return g_variant.load(); }
+extern "C" int lfd_mft_execution(const lfd_mft_desc *descs, int count) {
+    return (descs && count > 0) ? mft_resolve_execution(descs, count) : g_variant.load();
+}
 
 extern "C" size_t lfd_mft_workspace_bytes(const lfd_mft_desc *descs, int count) {
-    const int variant = g_variant.load();
-    if (variant == LFD_MFT_CZT) return czt_supported(descs, count) ? czt_workspace_bytes(descs, count) : folded_workspace_bytes(descs, count);
+    const int variant = mft_resolve_execution(descs, count);
+    if (variant == LFD_MFT_CZT) return czt_workspace_bytes(descs, count);
     if (variant == LFD_MFT_FOLDED) return folded_workspace_bytes(descs, count);
     size_t bytes = align_up((size_t)2 * count * sizeof(StageDesc), 256);
     for (int i = 0; i < count; ++i)
@@ -220,8 +232,8 @@ extern "C" int lfd_mft_c128_batched(const lfd_mft_desc *descs, int count, void *
     if (count == 0) return 0;
     LFD_REQUIRE(descs != nullptr && count > 0, "lfd_mft_c128_batched: bad descriptor array");
     LFD_REQUIRE(workspace != nullptr, "lfd_mft_c128_batched: workspace is NULL");
-    const int variant = g_variant.load();
-    if (variant == LFD_MFT_CZT && czt_supported(descs, count))
+    const int variant = mft_resolve_execution(descs, count);
+    if (variant == LFD_MFT_CZT)
         return launch_mft_czt(descs, count, workspace, workspace_bytes, stream, nullptr, 0);
     if (variant != LFD_MFT_DIRECT)
         return launch_mft_folded(descs, count, workspace, workspace_bytes, stream, nullptr, 0);

@@ -208,8 +208,11 @@ czt_tables_kernel(const Plane *__restrict__ descs) {
 // ---- one stage: every row of every plane whose FFT length is L ----------------------------------------------
 // STAGE_A: row i of f (n elements, or the fused phasor) -> Gt[:, i] (N outputs, transposed store)
 // else   : row v of Gt (m elements)                     -> out[:, v] (M outputs; complex128 or |.|^2 float64)
+// resident CTAs the register allocation must allow: ~768 threads per SM (3 CTAs of the 2048-point transform)
+constexpr int min_ctas(int log2l) { return (1 << log2l) / 8 >= 768 ? 1 : (768 / ((1 << log2l) / 8) > 16 ? 16 : 768 / ((1 << log2l) / 8)); }
+
 template <int LOG2L, bool STAGE_A>
-__global__ void __launch_bounds__((1 << LOG2L) / 8)
+__global__ void __launch_bounds__((1 << LOG2L) / 8, min_ctas(LOG2L))
 czt_stage_kernel(const Plane *__restrict__ descs, int count, int max_rows) {
     constexpr int L = 1 << LOG2L, T = L / 8;
     extern __shared__ double2 sm[];
@@ -271,6 +274,17 @@ using namespace czt;
 bool czt_supported(const lfd_mft_desc *descs, int count) {
     for (int i = 0; i < count; ++i)
         if (log2_len(descs[i].n, descs[i].N) > MAX_LOG2L || log2_len(descs[i].m, descs[i].M) > MAX_LOG2L) return false;
+    return true;
+}
+
+// LFD_MFT_AUTO: chirp-z where it is measured faster than the folded DMMA form — every plane has a 2048- or 4096-point
+// transform on at least one axis (1001^2 -> 1024^2: 70 us against 124 us; at 1024 points the two are level, cfg4)
+bool czt_preferred(const lfd_mft_desc *descs, int count) {
+    if (!czt_supported(descs, count)) return false;
+    for (int i = 0; i < count; ++i) {
+        const int la = log2_len(descs[i].n, descs[i].N), lb = log2_len(descs[i].m, descs[i].M);
+        if ((la > lb ? la : lb) < 11) return false;
+    }
     return true;
 }
 

@@ -61,14 +61,20 @@ def mft_flops(descs, count):
 
 
 def mft_flops_executed(descs, count):
-    """Real flops the DMMA pipe actually executes for a batch (unpadded): the folded variant runs
-    two real x complex GEMMs of ceil(M/2) x ceil(K/2) per stage, the direct one a complex x complex
-    GEMM of M x K."""
-    folded = _lib.lib().lfd_get_mft_variant() == 1
+    """Real FP64 flops a batch executes (unpadded) under the execution the library picks for it: the folded form runs
+    two real x complex GEMMs of ceil(M/2) x ceil(K/2) per stage, the direct one a complex x complex GEMM of M x K, the
+    chirp-z form two FFTs of length L (5 L log2 L each) and three point-wise complex products per row transform."""
+    execution = _lib.lib().lfd_mft_execution(descs, count)
     tot = 0.0
     for i in range(count):
         d = descs[i]
-        if folded:
+        if execution == 2:
+            for rows, nin, nout in ((d.m, d.n, d.N), (d.N, d.m, d.M)):
+                lg = 6
+                while (1 << lg) < nin + nout - 1:
+                    lg += 1
+                tot += rows * (2 * 5.0 * (1 << lg) * lg + 6.0 * ((1 << lg) + nin + nout))
+        elif execution == 1:
             h = lambda v: (v + 1) // 2
             tot += 8.0 * d.n * h(d.M) * h(d.m) + 8.0 * d.M * h(d.N) * h(d.n)
         else:

@@ -319,7 +319,7 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
         # With one field point every phasor feeds exactly one transform: K1 is then fused into the fold
         # kernel of the folded K2a / of K2b (lfd_mft_c128_from_pupil, lfd_mft_c64x3_from_pupil) and phasors never exist in HBM; with a single
         # segment the column stage also squares the field itself (no coherent merge to do in K3).
-        fused = P == 1 and (c64 or _lib.lib().lfd_get_mft_variant() in (1, 2))
+        fused = P == 1 and (c64 or _lib.lib().lfd_get_mft_variant() != 0)      # every execution but the direct one fuses K1
         intensity_out = fused and nseg == 1
         if not fused:
             phasors = torch.empty(nw, ops['total'], dtype=cdtype, device=device.device())

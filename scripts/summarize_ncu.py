@@ -46,7 +46,11 @@ def full(path):
             "launch__grid_size", "launch__block_size", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
             "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct",
-            "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.avg", "smsp__cycles_active.avg"]
+            "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.avg", "smsp__cycles_active.avg",
+            "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__occupancy_limit_registers",
+            "launch__occupancy_limit_shared_mem"]
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     res = []
     for r in data:
@@ -72,7 +76,17 @@ if __name__ == "__main__":
     json.dump(L, open(os.path.join(ROOT, "profiles", f"{tag}_launches.json"), "w"), indent=1)
     F = full(ppath)
     json.dump(F, open(os.path.join(ROOT, "profiles", f"{tag}_mft_ncu.json"), "w"), indent=1)
-    mft = [d for d in F if "mft" in d["kernel"]]
+    czt = [d for d in F if "czt_stage" in d["kernel"]]
+    if czt:
+        # one stage-A and one stage-B launch of NPLANES planes each: DRAM bytes of both stages per plane
+        tr = sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in czt) / (len(czt) / 2)
+        json.dump({"dram_bytes_per_launch_pair": tr, "planes_per_profiled_launch": NPLANES, "dram_bytes_per_plane": tr / NPLANES,
+                   "source": f"profiles/{tag}_mft_ncu.json",
+                   "note": f"ncu --set full on scripts/ncu_target.py ({NPLANES} planes 1001^2->1024^2 per launch), czt_stage_kernel A + B",
+                   "fp64_pipe_active_pct": sum(d.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", 0) for d in czt) / len(czt),
+                   "l1tex_throughput_pct": sum(d.get("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", 0) for d in czt) / len(czt)},
+                  open(os.path.join(ROOT, "profiles", "czt_ncu_summary.json"), "w"), indent=1)
+    mft = [d for d in F if "mft_folded" in d["kernel"]]
     if mft:
         tr = sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in mft) / len(mft)
         json.dump({"dram_bytes_per_launch": tr, "planes_per_profiled_launch": NPLANES,

@@ -54,12 +54,12 @@ def unpack_fields(d, prefix):
 TOL64 = 1e-10
 
 
-@pytest.fixture(params=["folded", "direct", "czt"])
+@pytest.fixture(params=["folded", "direct", "czt", "auto"])
 def mft_variant(request):
-    """Run a test under both executions of K2a (LFD_MFT_FOLDED is the default, LFD_MFT_DIRECT the
-    plain complex x complex form); restores the default afterwards."""
+    """Run a test under both executions of K2a (LFD_MFT_AUTO is the default: chirp-z for 2048/4096-point planes, else
+    the folded DMMA form; LFD_MFT_DIRECT is the plain complex x complex form); restores the default afterwards."""
     from lentil_b200 import _lib
     L = _lib.lib()
-    L.lfd_set_mft_variant({"direct": 0, "folded": 1, "czt": 2}[request.param])
+    L.lfd_set_mft_variant({"direct": 0, "folded": 1, "czt": 2, "auto": 3}[request.param])
     yield request.param
-    L.lfd_set_mft_variant(1)
+    L.lfd_set_mft_variant(3)
