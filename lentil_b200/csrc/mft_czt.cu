@@ -9,7 +9,7 @@
 // kernel executes (16.6 GFLOP algorithmic); exact for any alpha / shift / offset / parity like the other executions.
 //
 //  * every chirp phase is formed in cycles with error-free products and reduced exactly before sincospi (cis_cycles),
-//    the FFT roots come from a table of exactly reduced sincospi values: parity vs the oracle ~1e-13.
+//    the FFT twiddles come from per-pass tables of exactly reduced sincospi values: parity vs the oracle ~1e-13.
 //  * FFT: Stockham auto-sort in shared memory, radix 8 passes (+ one radix 4 or 2 pass), L/8 threads, one butterfly per
 //    thread and pass, two padded buffers (one 16-byte element of padding per 8: the stride-8 stores of the first pass
 //    are bank-conflict free).
@@ -25,15 +25,26 @@ namespace lfd {
 namespace czt {
 
 constexpr int MAX_LOG2L = 12, MIN_LOG2L = 6;
-constexpr int ROOTS = 1 << MAX_LOG2L;
-__device__ double2 g_roots[ROOTS];               // exp(-2 pi i t / 4096), t = 0 .. 4095 (exactly reduced)
+// Pass twiddles, one contiguous run per (FFT length, pass): g_tw[lg][(Ns - 1) / 7 + k] = exp(-2 pi i k / (Ns R)) for the pass
+// whose sub-transform length is Ns = 8^p (R = 8, or the 4 / 2 of the last pass), k = 0 .. Ns - 1.  Consecutive butterflies
+// read consecutive entries (a warp: 512 contiguous bytes) instead of gathering from one table of L-th roots.
+constexpr int TW_PER_LEN = 1024;                 // 1 + 8 + 64 + 512 = 585 entries for the longest transform
+__device__ double2 g_tw[MAX_LOG2L + 1][TW_PER_LEN];
 
 __global__ void roots_kernel() {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ROOTS) return;
-    double s, c;
-    sincospi(-2.0 * (double)t / (double)ROOTS, &s, &c);      // t / 4096 is exact
-    g_roots[t] = make_double2(c, s);
+    const int lg = MIN_LOG2L + blockIdx.y;
+    const int npass = lg / 3 + (lg % 3 ? 1 : 0), rlast = lg % 3 == 0 ? 8 : (lg % 3 == 2 ? 4 : 2);
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    int Ns = 1, off = 0;
+    for (int p = 0; p < npass; ++p) {
+        if (e >= off && e < off + Ns) {
+            const int k = e - off, R = (p == npass - 1) ? rlast : 8;
+            double s, c;
+            sincospi(-2.0 * (double)k / (double)(Ns * R), &s, &c);      // k / (Ns R) is exact (power-of-two denominator)
+            g_tw[lg][e] = make_double2(c, s);
+        }
+        off += Ns; Ns *= 8;
+    }
 }
 
 struct Plane {
@@ -100,7 +111,7 @@ __device__ __forceinline__ void pass(const In &in, const Out &out, int j, int Ns
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = in(j + r * (L / R));
     if (Ns > 1) {
-        double2 w1 = g_roots[k * (L / (Ns * R)) * (ROOTS / L)];
+        double2 w1 = g_tw[LOG2L][(Ns - 1) / 7 + k];
         if (S < 0) w1.y = -w1.y;
         double2 w = w1;
 #pragma unroll
@@ -354,7 +365,7 @@ int launch_mft_czt(const lfd_mft_desc *descs, int count, void *workspace, size_t
         static bool ready[64] = {false};
         std::lock_guard<std::mutex> lock(mu);
         if (dev < 64 && !ready[dev]) {
-            roots_kernel<<<ROOTS / 256, 256, 0, stream>>>();
+            roots_kernel<<<dim3(TW_PER_LEN / 256, MAX_LOG2L - MIN_LOG2L + 1), 256, 0, stream>>>();
             LFD_CUDA_OK(cudaGetLastError());
             LFD_CUDA_OK(cudaStreamSynchronize(stream));
             count_launch();
