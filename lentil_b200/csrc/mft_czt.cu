@@ -164,6 +164,93 @@ __device__ __forceinline__ void fft(double2 *a, double2 *b, int t, const In &fir
     __syncthreads();
 }
 
+// The adjoint of a forward pass: reads where the forward pass writes, takes the conjugate butterfly, multiplies by the
+// conjugate twiddles and writes where the forward pass reads.  The forward passes in reverse order, each replaced by its
+// adjoint, are the conjugate (= unnormalised inverse) transform — and the first of them reads exactly the elements the
+// last forward pass of the same thread produced, so that hand-over needs no trip through shared memory.
+template <int R, int LOG2L, class In, class Out>
+__device__ __forceinline__ void pass_adj(const In &in, const Out &out, int j, int Ns) {
+    constexpr int L = 1 << LOG2L;
+    const int k = j & (Ns - 1);
+    const int j0 = (j - k) * R + k;
+    double2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = in(j0 + r * Ns);
+    if constexpr (R == 8) dft8<-1>(v);
+    else if constexpr (R == 4) dft4<-1>(v[0], v[1], v[2], v[3]);
+    else dft2p<-1>(v[0], v[1]);
+    if (Ns > 1) {
+        double2 w1 = g_tw[LOG2L][(Ns - 1) / 7 + k];
+        w1.y = -w1.y;
+        double2 w = w1;
+#pragma unroll
+        for (int r = 1; r < R; ++r) { v[r] = cmul(v[r], w); if (r + 1 < R) w = cmul(w, w1); }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) out(j + r * (L / R), v[r]);
+}
+
+// last forward pass, product with H and first adjoint pass of one butterfly, in registers and in place in `buf`
+template <int R, int LOG2L>
+__device__ __forceinline__ void pass_turn(double2 *buf, const double2 *__restrict__ H, int j, int Ns) {
+    constexpr int L = 1 << LOG2L;
+    const int k = j & (Ns - 1);
+    const int j0 = (j - k) * R + k;
+    double2 v[R], w[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = buf[P(j + r * (L / R))];
+    const double2 w1 = g_tw[LOG2L][(Ns - 1) / 7 + k];
+    w[1] = w1;
+#pragma unroll
+    for (int r = 2; r < R; ++r) w[r] = cmul(w[r - 1], w1);
+#pragma unroll
+    for (int r = 1; r < R; ++r) v[r] = cmul(v[r], w[r]);
+    if constexpr (R == 8) dft8<1>(v);
+    else if constexpr (R == 4) dft4<1>(v[0], v[1], v[2], v[3]);
+    else dft2p<1>(v[0], v[1]);
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = cmul(v[r], H[j0 + r * Ns]);
+    if constexpr (R == 8) dft8<-1>(v);
+    else if constexpr (R == 4) dft4<-1>(v[0], v[1], v[2], v[3]);
+    else dft2p<-1>(v[0], v[1]);
+#pragma unroll
+    for (int r = 1; r < R; ++r) v[r] = cmul(v[r], make_double2(w[r].x, -w[r].y));
+#pragma unroll
+    for (int r = 0; r < R; ++r) buf[P(j + r * (L / R))] = v[r];
+}
+
+// One row of the chirp-z convolution: y = IFFT(FFT(x) * H), x through `load` (global memory), y through `store`.
+template <int LOG2L, class In, class Out>
+__device__ __forceinline__ void czt_row(double2 *a, double2 *b, int t, const In &load, const double2 *__restrict__ H, const Out &store) {
+    constexpr int T = (1 << LOG2L) / 8, N8 = LOG2L / 3, REM = LOG2L % 3, NPASS = N8 + (REM ? 1 : 0);
+    constexpr int RLAST = REM == 0 ? 8 : (REM == 2 ? 4 : 2);
+    static_assert(NPASS >= 2, "at least two passes");
+    int Ns = 1;
+    pass_all<8, 1, LOG2L>(load, SmemOut{a}, t, Ns);
+    __syncthreads();
+    Ns *= 8;
+    double2 *src = a, *dst = b;
+#pragma unroll
+    for (int p = 1; p < NPASS - 1; ++p) {
+        pass_all<8, 1, LOG2L>(SmemIn{src}, SmemOut{dst}, t, Ns);
+        __syncthreads();
+        double2 *x = src; src = dst; dst = x;
+        Ns *= 8;
+    }
+#pragma unroll
+    for (int q = 0; q < 8 / RLAST; ++q) pass_turn<RLAST, LOG2L>(src, H, t + q * T, Ns);
+    __syncthreads();
+#pragma unroll
+    for (int p = NPASS - 2; p >= 1; --p) {
+        Ns /= 8;
+        pass_adj<8, LOG2L>(SmemIn{src}, SmemOut{dst}, t, Ns);
+        __syncthreads();
+        double2 *x = src; src = dst; dst = x;
+    }
+    pass_adj<8, LOG2L>(SmemIn{src}, store, t, 1);
+    __syncthreads();
+}
+
 __device__ __forceinline__ double2 pupil_phasor(const Plane &d, int i, int c) {
     const long long pix = (long long)(d.pr0 + i) * d.pld + (d.pc0 + c);
     double a = d.amp[pix];
@@ -248,24 +335,20 @@ czt_stage_kernel(const Plane *__restrict__ descs, int count, int max_rows) {
             else x = dp->Gt[(long long)row * dp->mpad + i];
             return cmul(x, pre[i]);
         };
-        double2 *spec = fft_result_buffer<LOG2L>(a, b);               // where the spectrum (x H) lands
-        double2 *other = (spec == a) ? b : a;
-        fft<1, LOG2L>(a, b, t, load, SmemTimesH{spec, H});
-        // inverse transform: reads the spectrum, ping-pongs starting with `other`, last pass goes to global memory
         if (STAGE_A) {
             double2 *Gt = dp->Gt; const long long mpad = dp->mpad;
             auto store = [=](int i, double2 v) { if (i < nout) Gt[(long long)i * mpad + row] = cmul(v, post[i]); };
-            fft<-1, LOG2L>(other, spec, t, SmemIn{spec}, store);
+            czt_row<LOG2L>(a, b, t, load, H, store);
         } else if (dp->intensity) {
             double *out = (double *)dp->out; const long long ldo = dp->ldo;
             auto store = [=](int i, double2 v) {
                 if (i < nout) { const double2 z = cmul(v, post[i]); out[(long long)i * ldo + row] = z.x * z.x + z.y * z.y; }
             };
-            fft<-1, LOG2L>(other, spec, t, SmemIn{spec}, store);
+            czt_row<LOG2L>(a, b, t, load, H, store);
         } else {
             double2 *out = (double2 *)dp->out; const long long ldo = dp->ldo;
             auto store = [=](int i, double2 v) { if (i < nout) out[(long long)i * ldo + row] = cmul(v, post[i]); };
-            fft<-1, LOG2L>(other, spec, t, SmemIn{spec}, store);
+            czt_row<LOG2L>(a, b, t, load, H, store);
         }
     }
 }
