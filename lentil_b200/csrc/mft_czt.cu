@@ -103,15 +103,17 @@ struct SmemTimesH {
 
 // One Stockham pass of radix R over a length-L sequence for butterfly j: reads in(j + r L/R), multiplies by the pass
 // twiddles exp(-+ 2 pi i r k / (Ns R)), k = j mod Ns, takes the R-point DFT and writes out((j - k) R + k + r Ns).
+// twiddle of butterfly j in the pass with sub-transform length Ns (callers fetch it before the barrier that precedes the pass)
+template <int LOG2L> __device__ __forceinline__ double2 pass_twiddle(int j, int Ns) { return g_tw[LOG2L][(Ns - 1) / 7 + (j & (Ns - 1))]; }
+
 template <int R, int S, int LOG2L, class In, class Out>
-__device__ __forceinline__ void pass(const In &in, const Out &out, int j, int Ns) {
+__device__ __forceinline__ void pass(const In &in, const Out &out, int j, int Ns, double2 w1 = make_double2(1.0, 0.0)) {
     constexpr int L = 1 << LOG2L;
     const int k = j & (Ns - 1);
     double2 v[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = in(j + r * (L / R));
     if (Ns > 1) {
-        double2 w1 = g_tw[LOG2L][(Ns - 1) / 7 + k];
         if (S < 0) w1.y = -w1.y;
         double2 w = w1;
 #pragma unroll
@@ -130,7 +132,7 @@ template <int R, int S, int LOG2L, class In, class Out>
 __device__ __forceinline__ void pass_all(const In &in, const Out &out, int t, int Ns) {
     constexpr int T = (1 << LOG2L) / 8;
 #pragma unroll
-    for (int q = 0; q < 8 / R; ++q) pass<R, S, LOG2L>(in, out, t + q * T, Ns);
+    for (int q = 0; q < 8 / R; ++q) pass<R, S, LOG2L>(in, out, t + q * T, Ns, pass_twiddle<LOG2L>(t + q * T, Ns));
 }
 
 // FFT of L elements with L / 8 threads.  The first pass reads through `first` (shared memory or a functor that loads
@@ -169,7 +171,7 @@ __device__ __forceinline__ void fft(double2 *a, double2 *b, int t, const In &fir
 // adjoint, are the conjugate (= unnormalised inverse) transform — and the first of them reads exactly the elements the
 // last forward pass of the same thread produced, so that hand-over needs no trip through shared memory.
 template <int R, int LOG2L, class In, class Out>
-__device__ __forceinline__ void pass_adj(const In &in, const Out &out, int j, int Ns) {
+__device__ __forceinline__ void pass_adj(const In &in, const Out &out, int j, int Ns, double2 w1) {
     constexpr int L = 1 << LOG2L;
     const int k = j & (Ns - 1);
     const int j0 = (j - k) * R + k;
@@ -180,7 +182,6 @@ __device__ __forceinline__ void pass_adj(const In &in, const Out &out, int j, in
     else if constexpr (R == 4) dft4<-1>(v[0], v[1], v[2], v[3]);
     else dft2p<-1>(v[0], v[1]);
     if (Ns > 1) {
-        double2 w1 = g_tw[LOG2L][(Ns - 1) / 7 + k];
         w1.y = -w1.y;
         double2 w = w1;
 #pragma unroll
@@ -192,14 +193,13 @@ __device__ __forceinline__ void pass_adj(const In &in, const Out &out, int j, in
 
 // last forward pass, product with H and first adjoint pass of one butterfly, in registers and in place in `buf`
 template <int R, int LOG2L>
-__device__ __forceinline__ void pass_turn(double2 *buf, const double2 *__restrict__ H, int j, int Ns) {
+__device__ __forceinline__ void pass_turn(double2 *buf, const double2 *__restrict__ H, int j, int Ns, double2 w1) {
     constexpr int L = 1 << LOG2L;
     const int k = j & (Ns - 1);
     const int j0 = (j - k) * R + k;
     double2 v[R], w[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = buf[P(j + r * (L / R))];
-    const double2 w1 = g_tw[LOG2L][(Ns - 1) / 7 + k];
     w[1] = w1;
 #pragma unroll
     for (int r = 2; r < R; ++r) w[r] = cmul(w[r - 1], w1);
@@ -219,35 +219,49 @@ __device__ __forceinline__ void pass_turn(double2 *buf, const double2 *__restric
     for (int r = 0; r < R; ++r) buf[P(j + r * (L / R))] = v[r];
 }
 
-// One row of the chirp-z convolution: y = IFFT(FFT(x) * H), x through `load` (global memory), y through `store`.
-template <int LOG2L, class In, class Out>
-__device__ __forceinline__ void czt_row(double2 *a, double2 *b, int t, const In &load, const double2 *__restrict__ H, const Out &store) {
+// One row of the chirp-z convolution: y = IFFT(FFT(x) * H).  `load8(j, v)` fills v[r] with x[j + r L/8] (global memory,
+// all eight loads issued before any arithmetic), y leaves through `store`.  The twiddle of the next pass is fetched
+// before the barrier that precedes it, so its latency overlaps the barrier wait.
+template <int LOG2L, class Load8, class Out>
+__device__ __forceinline__ void czt_row(double2 *a, double2 *b, int t, const Load8 &load8, const double2 *__restrict__ H, const Out &store) {
     constexpr int T = (1 << LOG2L) / 8, N8 = LOG2L / 3, REM = LOG2L % 3, NPASS = N8 + (REM ? 1 : 0);
     constexpr int RLAST = REM == 0 ? 8 : (REM == 2 ? 4 : 2);
     static_assert(NPASS >= 2, "at least two passes");
-    int Ns = 1;
-    pass_all<8, 1, LOG2L>(load, SmemOut{a}, t, Ns);
-    __syncthreads();
-    Ns *= 8;
+    int Ns = 8;
+    {   // first pass (Ns = 1: no twiddles): global -> registers -> a
+        double2 v[8];
+        load8(t, v);
+        dft8<1>(v);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) a[P(8 * t + r)] = v[r];
+    }
     double2 *src = a, *dst = b;
 #pragma unroll
     for (int p = 1; p < NPASS - 1; ++p) {
-        pass_all<8, 1, LOG2L>(SmemIn{src}, SmemOut{dst}, t, Ns);
+        const double2 w1 = pass_twiddle<LOG2L>(t, Ns);
         __syncthreads();
+        pass<8, 1, LOG2L>(SmemIn{src}, SmemOut{dst}, t, Ns, w1);
         double2 *x = src; src = dst; dst = x;
         Ns *= 8;
     }
+    {
+        double2 wt[8 / RLAST];
 #pragma unroll
-    for (int q = 0; q < 8 / RLAST; ++q) pass_turn<RLAST, LOG2L>(src, H, t + q * T, Ns);
-    __syncthreads();
+        for (int q = 0; q < 8 / RLAST; ++q) wt[q] = pass_twiddle<LOG2L>(t + q * T, Ns);
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 8 / RLAST; ++q) pass_turn<RLAST, LOG2L>(src, H, t + q * T, Ns, wt[q]);
+    }
 #pragma unroll
     for (int p = NPASS - 2; p >= 1; --p) {
         Ns /= 8;
-        pass_adj<8, LOG2L>(SmemIn{src}, SmemOut{dst}, t, Ns);
+        const double2 w1 = pass_twiddle<LOG2L>(t, Ns);
         __syncthreads();
+        pass_adj<8, LOG2L>(SmemIn{src}, SmemOut{dst}, t, Ns, w1);
         double2 *x = src; src = dst; dst = x;
     }
-    pass_adj<8, LOG2L>(SmemIn{src}, store, t, 1);
+    __syncthreads();
+    pass_adj<8, LOG2L>(SmemIn{src}, store, t, 1, make_double2(1.0, 0.0));
     __syncthreads();
 }
 
@@ -317,9 +331,20 @@ czt_stage_kernel(const Plane *__restrict__ descs, int count, int max_rows) {
     double2 *a = sm, *b = sm + (L + L / 8);
     const int t = threadIdx.x;
     const long long total = (long long)count * max_rows;
+    __shared__ Plane sd;                 // the plane this CTA is working on (rows are dealt plane-major: it changes rarely)
+    int cur = -1;
     for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-        const Plane &d = descs[w / max_rows];
-        const int row = (int)(w % max_rows);
+        const int plane = (int)(w / max_rows);
+        const int row = (int)(w - (long long)plane * max_rows);
+        if (plane != cur) {              // uniform over the CTA
+            __syncthreads();
+            const unsigned long long *g = reinterpret_cast<const unsigned long long *>(descs + plane);
+            unsigned long long *sdw = reinterpret_cast<unsigned long long *>(&sd);
+            for (int i = t; i < (int)(sizeof(Plane) / 8); i += T) sdw[i] = g[i];
+            __syncthreads();
+            cur = plane;
+        }
+        const Plane &d = sd;
         const int nrows = STAGE_A ? d.m : d.N;
         if (row >= nrows || (STAGE_A ? d.logLA : d.logLB) != LOG2L) continue;     // uniform over the CTA
         const int nin = STAGE_A ? d.n : d.m, nout = STAGE_A ? d.N : d.M;
@@ -327,13 +352,47 @@ czt_stage_kernel(const Plane *__restrict__ descs, int count, int max_rows) {
         const double2 *__restrict__ post = STAGE_A ? d.postA : d.postB;
         const double2 *__restrict__ H = STAGE_A ? d.HA : d.HB;
         const Plane *dp = &d;
-        // first forward pass reads the row straight from global memory (x pre-chirp; zero beyond the input length)
-        auto load = [=](int i) -> double2 {
-            if (i >= nin) return make_double2(0.0, 0.0);
-            double2 x;
-            if (STAGE_A) x = dp->amp != nullptr ? pupil_phasor(*dp, row, i) : dp->f[(long long)row * dp->ldf + i];
-            else x = dp->Gt[(long long)row * dp->mpad + i];
-            return cmul(x, pre[i]);
+        // first forward pass: the eight inputs of this thread straight from global memory (x pre-chirp; zero beyond the
+        // input length), every load issued before the arithmetic
+        auto load = [=](int j, double2 (&v)[8]) {
+            double2 pr[8];
+            if (STAGE_A && dp->amp != nullptr) {
+                double am[8], op[8];
+                const long long base = (long long)(dp->pr0 + row) * dp->pld + dp->pc0;
+                const unsigned char *mk = dp->mask;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int i = j + r * (L / 8);
+                    const bool in = i < nin;
+                    am[r] = in ? dp->amp[base + i] : 0.0;
+                    op[r] = in ? dp->opd[base + i] : 0.0;
+                    pr[r] = in ? pre[i] : make_double2(0.0, 0.0);
+                    if (in && mk != nullptr && mk[base + i] == 0) am[r] = 0.0;
+                }
+                const double lam = dp->wavelength;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    double2 x = make_double2(0.0, 0.0);
+                    if (am[r] != 0.0) {                        // same arithmetic as K1 (pupil_prep.cu): phase in cycles, reduced exactly
+                        const double tcyc = op[r] / lam;
+                        double sn, cs;
+                        sincospi(2.0 * (tcyc - rint(tcyc)), &sn, &cs);
+                        x = make_double2(am[r] * cs, am[r] * sn);
+                    }
+                    v[r] = cmul(x, pr[r]);
+                }
+            } else {
+                const double2 *src = STAGE_A ? dp->f + (long long)row * dp->ldf : dp->Gt + (long long)row * dp->mpad;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int i = j + r * (L / 8);
+                    const bool in = i < nin;
+                    v[r] = in ? src[i] : make_double2(0.0, 0.0);
+                    pr[r] = in ? pre[i] : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int r = 0; r < 8; ++r) v[r] = cmul(v[r], pr[r]);
+            }
         };
         if (STAGE_A) {
             double2 *Gt = dp->Gt; const long long mpad = dp->mpad;
