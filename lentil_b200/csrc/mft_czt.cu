@@ -430,13 +430,14 @@ bool czt_supported(const lfd_mft_desc *descs, int count) {
     return true;
 }
 
-// LFD_MFT_AUTO: chirp-z where it is measured faster than the folded DMMA form — every plane has a 2048- or 4096-point
-// transform on at least one axis (1001^2 -> 1024^2: 70 us against 124 us; at 1024 points the two are level, cfg4)
+// LFD_MFT_AUTO: chirp-z where it is measured faster than the folded DMMA form — every plane has a transform of 1024 points
+// or more on at least one axis (1001^2 -> 1024^2: 54 us against 121 us; 501^2 -> 512^2, cfg4: 14.3 against 19.3 us; the
+// 18 x 50 windows of cfg3: 9.5 against 12.6 ms).  Smaller planes (L <= 512: CTAs of 64 threads or fewer) stay on the folded form.
 bool czt_preferred(const lfd_mft_desc *descs, int count) {
     if (!czt_supported(descs, count)) return false;
     for (int i = 0; i < count; ++i) {
         const int la = log2_len(descs[i].n, descs[i].N), lb = log2_len(descs[i].m, descs[i].M);
-        if ((la > lb ? la : lb) < 11) return false;
+        if ((la > lb ? la : lb) < 10) return false;
     }
     return true;
 }
