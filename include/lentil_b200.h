@@ -70,8 +70,8 @@ typedef struct lfd_mft_desc {
 #define LFD_MFT_DIRECT 0
 #define LFD_MFT_FOLDED 1
 #define LFD_MFT_CZT    2
-#define LFD_MFT_AUTO   3   /* default: chirp-z when every plane of the batch has an FFT length of 1024 .. 4096 on one
-                            * of its axes (where it is measured faster than the folded form), else folded */
+#define LFD_MFT_AUTO   3   /* default: chirp-z whenever every plane of the batch fits it (FFT length <= 4096 on both axes;
+                            * measured faster than the folded form at every size from 128^2 to 2048^2), else folded */
 int lfd_set_mft_variant(int variant);
 int lfd_get_mft_variant(void);
 /* which execution (LFD_MFT_DIRECT / FOLDED / CZT) a batch runs under the current setting */

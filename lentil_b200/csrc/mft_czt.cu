@@ -430,17 +430,10 @@ bool czt_supported(const lfd_mft_desc *descs, int count) {
     return true;
 }
 
-// LFD_MFT_AUTO: chirp-z where it is measured faster than the folded DMMA form — every plane has a transform of 1024 points
-// or more on at least one axis (1001^2 -> 1024^2: 54 us against 121 us; 501^2 -> 512^2, cfg4: 14.3 against 19.3 us; the
-// 18 x 50 windows of cfg3: 9.5 against 12.6 ms).  Smaller planes (L <= 512: CTAs of 64 threads or fewer) stay on the folded form.
-bool czt_preferred(const lfd_mft_desc *descs, int count) {
-    if (!czt_supported(descs, count)) return false;
-    for (int i = 0; i < count; ++i) {
-        const int la = log2_len(descs[i].n, descs[i].N), lb = log2_len(descs[i].m, descs[i].M);
-        if ((la > lb ? la : lb) < 10) return false;
-    }
-    return true;
-}
+// LFD_MFT_AUTO: chirp-z wherever it can run.  Measured against the folded DMMA form on dense random planes, batched
+// (scripts/small_plane_timing.py, r01o): 121^2 -> 128^2 0.66 vs 0.73 us, 241^2 -> 256^2 2.9 vs 3.1 us, 501^2 -> 512^2 12.4 vs
+// 19.3 us, 1001^2 -> 1024^2 53.6 vs 139 us, 2001^2 -> 2048^2 251 vs 1036 us per plane; cfg3's 900 windows 9.5 vs 12.6 ms.
+bool czt_preferred(const lfd_mft_desc *descs, int count) { return czt_supported(descs, count); }
 
 size_t czt_workspace_bytes(const lfd_mft_desc *descs, int count) {
     size_t bytes = al((size_t)count * sizeof(Plane));
