@@ -195,7 +195,18 @@ def workload_config(n_gpus):
 
 
 # ------------------------------------------------------------------------------------------------
+def _private_stdout():
+    """stdout carries exactly ONE JSON line, but libraries write there too (NCCL prints its version banner on file
+    descriptor 1 when a communicator is created).  Keep a private duplicate of the real stdout for the JSON line and point
+    descriptor 1 at stderr for everything else."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def run_ours(args):
+    out_stream = _private_stdout()
     import torch
     import lentil_b200 as lentil
     from lentil_b200 import device, fourier
@@ -205,9 +216,6 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
-        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; stdout carries exactly one JSON line here
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -447,7 +455,7 @@ def run_ours(args):
         "c64_3xtf32": {"value": c64_value, "unit": "planes/s", "peak_normalised_error_vs_fp64": c64_err,
                        "note": "optional complex64 mode (K2b: tcgen05 kind::tf32, TMEM accumulators); gate 1e-5"},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=out_stream, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
