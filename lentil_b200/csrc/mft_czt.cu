@@ -95,14 +95,6 @@ template <int S> __device__ __forceinline__ void dft8(double2 (&v)[8]) {
 // Element sources / sinks of a pass: shared memory (padded layout), or the caller's functor (global memory).
 struct SmemIn  { const double2 *p; __device__ __forceinline__ double2 operator()(int i) const { return p[P(i)]; } };
 struct SmemOut { double2 *p; __device__ __forceinline__ void operator()(int i, double2 v) const { p[P(i)] = v; } };
-// last pass of the forward transform: the spectrum is multiplied by H on its way to shared memory
-struct SmemTimesH {
-    double2 *p; const double2 *__restrict__ H;
-    __device__ __forceinline__ void operator()(int i, double2 v) const { p[P(i)] = cmul(v, H[i]); }
-};
-
-// One Stockham pass of radix R over a length-L sequence for butterfly j: reads in(j + r L/R), multiplies by the pass
-// twiddles exp(-+ 2 pi i r k / (Ns R)), k = j mod Ns, takes the R-point DFT and writes out((j - k) R + k + r Ns).
 // twiddle of butterfly j in the pass with sub-transform length Ns (callers fetch it before the barrier that precedes the pass)
 template <int LOG2L> __device__ __forceinline__ double2 pass_twiddle(int j, int Ns) { return g_tw[LOG2L][(Ns - 1) / 7 + (j & (Ns - 1))]; }
 
@@ -135,15 +127,9 @@ __device__ __forceinline__ void pass_all(const In &in, const Out &out, int t, in
     for (int q = 0; q < 8 / R; ++q) pass<R, S, LOG2L>(in, out, t + q * T, Ns, pass_twiddle<LOG2L>(t + q * T, Ns));
 }
 
-// FFT of L elements with L / 8 threads.  The first pass reads through `first` (shared memory or a functor that loads
-// from global memory: the input never makes a separate trip through shared memory), the last pass writes through `last`
-// (shared memory, shared memory x H, or global memory); the passes in between ping-pong between the padded buffers a
-// and b, starting by WRITING a.  Every pass is followed by a __syncthreads().  Returns the buffer the last pass would
-// have written had it gone to shared memory (what `last` should point at when it is a shared-memory sink).
-template <int LOG2L> __device__ __forceinline__ double2 *fft_result_buffer(double2 *a, double2 *b) {
-    constexpr int NPASS = LOG2L / 3 + (LOG2L % 3 ? 1 : 0);
-    return (NPASS & 1) ? a : b;
-}
+// Plain FFT of L elements with L / 8 threads (used for the chirp filter H; the row transforms use czt_row below).  The first
+// pass reads through `first`, the last pass writes through `last` (functors: shared or global memory); the passes in
+// between ping-pong between the padded buffers a and b, starting by WRITING a.  Every pass is followed by a __syncthreads().
 template <int S, int LOG2L, class In, class Out>
 __device__ __forceinline__ void fft(double2 *a, double2 *b, int t, const In &first, const Out &last) {
     constexpr int N8 = LOG2L / 3, REM = LOG2L % 3, NPASS = N8 + (REM ? 1 : 0);
@@ -263,17 +249,6 @@ __device__ __forceinline__ void czt_row(double2 *a, double2 *b, int t, const Loa
     __syncthreads();
     pass_adj<8, LOG2L>(SmemIn{src}, store, t, 1, make_double2(1.0, 0.0));
     __syncthreads();
-}
-
-__device__ __forceinline__ double2 pupil_phasor(const Plane &d, int i, int c) {
-    const long long pix = (long long)(d.pr0 + i) * d.pld + (d.pc0 + c);
-    double a = d.amp[pix];
-    if (d.mask != nullptr && d.mask[pix] == 0) a = 0.0;
-    if (a == 0.0) return make_double2(0.0, 0.0);
-    const double tcyc = d.opd[pix] / d.wavelength;      // phase in cycles, reduced exactly
-    double sn, cs;
-    sincospi(2.0 * (tcyc - rint(tcyc)), &sn, &cs);
-    return make_double2(a * cs, a * sn);
 }
 
 // ---- per (plane, axis): pre / post chirps and the transformed chirp filter H = FFT_L(h) -----------------

@@ -223,3 +223,32 @@ def test_sparse_support_patterns(kind):
         assert not F.any()
     else:
         assert peak_err(F, ref) <= TOL64
+
+
+def test_chirpz_length_boundaries_and_fallback():
+    # the chirp-z execution pads each axis to the power of two >= n_in + n_out - 1 (64 .. 4096); beyond 4096 the library runs
+    # the folded DMMA form instead.  Rectangular planes keep the long axis cheap.
+    import ctypes as C
+    from lentil_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(41)
+    saved = L.lfd_get_mft_variant()
+    L.lfd_set_mft_variant(2)
+    try:
+        for (m, n), (M, N), expect in [((33, 32), (32, 33), 2),        # 64 exactly on both axes
+                                       ((32, 5), (34, 7), 2),          # 65 -> 128, 11 -> 64
+                                       ((2049, 8), (2048, 8), 2),      # 4096 exactly
+                                       ((2100, 8), (2048, 8), 1)]:     # 4147 > 4096: folded
+            d = (_lib.MftDesc * 1)()
+            d[0].m, d[0].n, d[0].M, d[0].N = m, n, M, N
+            assert L.lfd_mft_execution(d, 1) == expect, (m, n, M, N)
+            f = rng.normal(size=(m, n)) + 1j * rng.normal(size=(m, n))
+            alpha = (0.9 / max(m, M), 0.8 / max(n, N))
+            for kw in (dict(shift=(0.25, -1.5), offset=(3, -2)), dict(unitary=False)):
+                got = lentil.fourier.dft2(f, alpha, shape=(M, N), **kw)
+                ref = oc.dft2(f, alpha, shape=(M, N), **kw)
+                assert peak_err(got, ref) <= TOL64, (m, n, M, N, kw)
+            got = lentil.fourier.idft2(f, alpha, shape=(M, N), shift=(0.5, 0.0))
+            assert peak_err(got, oc.idft2(f, alpha, shape=(M, N), shift=(0.5, 0.0))) <= TOL64
+    finally:
+        L.lfd_set_mft_variant(saved)
