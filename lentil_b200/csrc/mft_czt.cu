@@ -13,6 +13,9 @@
 //  * FFT: Stockham auto-sort in shared memory, radix 8 passes (+ one radix 4 or 2 pass), L/8 threads, one butterfly per
 //    thread and pass, two padded buffers (one 16-byte element of padding per 8: the stride-8 stores of the first pass
 //    are bank-conflict free).
+//  * the inverse transform is run as the adjoints of the forward passes in reverse order, so the last forward pass, the
+//    product with H and the first inverse pass of a thread happen in registers (pass_turn); the first forward pass loads
+//    straight from global memory and the last inverse pass stores straight to it (czt_row).
 //  * stage A transforms the rows of f (contiguous loads; K1 can be fused: the phasor amp*mask*exp(2 pi i opd / lambda)
 //    is formed in the load, lentil/plane.py:502-507) and stores its result transposed, stage B transforms the rows of
 //    that (= the columns of the plane) and stores F, or |F|^2 as float64 when the caller only wants intensities.
