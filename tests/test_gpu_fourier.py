@@ -228,8 +228,6 @@ def test_sparse_support_patterns(kind):
 def test_chirpz_length_boundaries_and_fallback():
     # the chirp-z execution pads each axis to the power of two >= n_in + n_out - 1 (64 .. 4096); beyond 4096 the library runs
     # the folded DMMA form instead.  Rectangular planes keep the long axis cheap.
-    import ctypes as C
-    from lentil_b200 import _lib
     L = _lib.lib()
     rng = np.random.default_rng(41)
     saved = L.lfd_get_mft_variant()
