@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblentil_b200.so")
+# LFD_LIB: development aid — load a tagged build (python -m lentil_b200.csrc.build --tag ...) instead of the production library
+LIB_PATH = os.environ.get("LFD_LIB") or os.path.join(_HERE, "liblentil_b200.so")
 
 _lib = None
 

@@ -132,7 +132,7 @@ extern "C" int lfd_field_mul(const void *a, int64_t lda, const void *b, int64_t 
     LFD_REQUIRE(a && out && h > 0 && w > 0 && lda >= w && ldo >= w && (!b || ldb >= w),
                 "lfd_field_mul: bad arguments");
     long long n = (long long)h * w, blocks = (n + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > lfd::sm_or_default() * 8) blocks = lfd::sm_or_default() * 8;
     lfd::field_mul_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         (const double2 *)a, lda, (const double2 *)b, ldb, s_re, s_im, (double2 *)out, ldo, h, w);
     LFD_CUDA_OK(cudaGetLastError());

@@ -4,6 +4,9 @@
 
 #include <string.h>
 #include <stdlib.h>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace lfd {
 
@@ -15,6 +18,36 @@ void set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+static std::mutex g_dev_mu;
+static std::map<std::pair<int, const void *>, int> g_smem_set;      // (device, kernel) -> bytes granted
+static std::map<int, int> g_sm_count;
+
+int ensure_dynamic_smem(int device, const void *kernel, int bytes) {
+    std::lock_guard<std::mutex> lock(g_dev_mu);
+    auto key = std::make_pair(device, kernel);
+    auto it = g_smem_set.find(key);
+    if (it != g_smem_set.end() && it->second >= bytes) return 0;
+    LFD_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    g_smem_set[key] = bytes;
+    return 0;
+}
+
+int sm_count(int device) {
+    std::lock_guard<std::mutex> lock(g_dev_mu);
+    auto it = g_sm_count.find(device);
+    if (it != g_sm_count.end()) return it->second;
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) return 0;
+    g_sm_count[device] = n;
+    return n;
+}
+
+int current_sm_count() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    return sm_count(dev);
 }
 
 }  // namespace lfd

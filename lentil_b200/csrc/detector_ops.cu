@@ -75,7 +75,7 @@ opd_synth_kernel(const double *__restrict__ basis, const double *__restrict__ co
 
 static inline unsigned grid_for(long long n) {
     long long b = (n + 255) / 256;
-    return (unsigned)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
+    return (unsigned)(b > sm_or_default() * 16 ? sm_or_default() * 16 : (b < 1 ? 1 : b));
 }
 
 }  // namespace lfd

@@ -125,7 +125,7 @@ extern "C" int lfd_mask_bbox(const void *x, int32_t is_f64, int32_t nonzero, int
     LFD_REQUIRE(x && out_dev && n_r > 0 && n_c > 0 && nplanes > 0, "lfd_mask_bbox: bad arguments");
     bbox_init_kernel<<<(nplanes + 127) / 128, 128, 0, stream>>>(out_dev, nplanes, n_r, n_c);
     long long npix = (long long)n_r * n_c, bx = (npix + 255) / 256;
-    if (bx > 148 * 8) bx = 148 * 8;
+    if (bx > sm_or_default() * 8) bx = sm_or_default() * 8;
     dim3 grid((unsigned)bx, (unsigned)nplanes);
     if (is_f64) bbox_kernel<double><<<grid, 256, 0, stream>>>((const double *)x, n_r, n_c, nonzero, out_dev);
     else bbox_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t *)x, n_r, n_c, nonzero, out_dev);
@@ -157,7 +157,7 @@ extern "C" int lfd_fit_tilt_moments(const double *opd, const uint8_t *mask, cons
     LFD_CUDA_OK(e);
     LFD_CUDA_OK(cudaMemsetAsync(moments_dev, 0, (size_t)nseg * FT_MOMENTS * sizeof(double), stream));
     long long bx = (max_elem + 255) / 256;
-    if (bx > 148 * 4) bx = 148 * 4;
+    if (bx > sm_or_default() * 4) bx = sm_or_default() * 4;
     fit_tilt_moments_kernel<<<dim3((unsigned)bx, (unsigned)nseg), 256, 0, stream>>>(
         opd, mask, amp_for_mask, n_r, n_c, dx0, dx1, (const FitSeg *)scratch_dev, moments_dev);
     LFD_CUDA_OK(cudaGetLastError());
@@ -171,7 +171,7 @@ extern "C" int lfd_remove_tilt(const double *opd, const uint8_t *mask, const dou
     LFD_REQUIRE(opd && (mask || amp_for_mask) && coef_dev && out && nseg > 0, "lfd_remove_tilt: bad arguments");
     LFD_REQUIRE(nseg == 1 || mask, "lfd_remove_tilt: segmented planes need a mask cube");
     long long npix = (long long)n_r * n_c, bx = (npix + 255) / 256;
-    if (bx > 148 * 16) bx = 148 * 16;
+    if (bx > sm_or_default() * 16) bx = sm_or_default() * 16;
     remove_tilt_kernel<<<(unsigned)bx, 256, 0, (cudaStream_t)stream>>>(opd, mask, amp_for_mask, n_r, n_c, nseg, dx0, dx1,
                                                                       coef_dev, out);
     LFD_CUDA_OK(cudaGetLastError());

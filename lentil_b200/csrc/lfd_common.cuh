@@ -15,6 +15,15 @@ void set_error(const char *fmt, ...);
 extern std::atomic<uint64_t> g_launches;
 inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Per-DEVICE bookkeeping (a process may drive several GPUs; cudaFuncSetAttribute applies to the current device only).
+// ensure_dynamic_smem raises a kernel's dynamic shared-memory limit once per (device, kernel); sm_count caches
+// cudaDevAttrMultiProcessorCount.  Both are thread-safe; ensure_dynamic_smem returns non-zero (error set) on failure.
+int ensure_dynamic_smem(int device, const void *kernel, int bytes);
+int sm_count(int device);
+int current_sm_count();          // of the calling thread's current device; 0 on error
+// grid-size cap helper: SMs of the current device (148 on B200); never 0
+inline int sm_or_default() { const int n = current_sm_count(); return n > 0 ? n : 148; }
+
 #define LFD_CUDA_OK(expr)                                                                   \
     do {                                                                                    \
         cudaError_t e__ = (expr);                                                           \

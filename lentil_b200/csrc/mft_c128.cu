@@ -241,12 +241,9 @@ extern "C" int lfd_mft_c128_batched(const lfd_mft_desc *descs, int count, void *
     LFD_REQUIRE(workspace_bytes >= need, "lfd_mft_c128_batched: workspace too small (%zu < %zu)",
                 workspace_bytes, need);
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        LFD_CUDA_OK(cudaFuncSetAttribute(mft_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)SMEM_BYTES));
-        attr_set = true;
-    }
+    int dev = 0;
+    LFD_CUDA_OK(cudaGetDevice(&dev));
+    if (ensure_dynamic_smem(dev, (const void *)mft_stage_kernel, (int)SMEM_BYTES)) return 1;
 
     StageDesc *h = (StageDesc *)malloc((size_t)2 * count * sizeof(StageDesc));
     LFD_REQUIRE(h != nullptr, "out of host memory");

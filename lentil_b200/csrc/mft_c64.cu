@@ -762,12 +762,10 @@ int launch_mft_c64(const lfd_mft_desc *descs, int count, void *workspace, size_t
     LFD_REQUIRE(count <= 32767, "lfd_mft_c64x3_batched: at most 32767 planes per call (got %d)", count);
     const size_t need = c64_workspace_bytes(descs, count);
     LFD_REQUIRE(workspace_bytes >= need, "lfd_mft_c64x3_batched: workspace too small (%zu < %zu)", workspace_bytes, need);
-    static bool attr_set = false;
-    if (!attr_set) {
-        LFD_CUDA_OK(cudaFuncSetAttribute(mft_c64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        LFD_CUDA_OK(cudaFuncSetAttribute(mft_c64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        attr_set = true;
-    }
+    int dev = 0;
+    LFD_CUDA_OK(cudaGetDevice(&dev));
+    if (ensure_dynamic_smem(dev, (const void *)mft_c64_kernel<true>, (int)SMEM_BYTES)) return 1;
+    if (ensure_dynamic_smem(dev, (const void *)mft_c64_kernel<false>, (int)SMEM_BYTES)) return 1;
     const size_t desc_bytes = (size_t)count * (sizeof(FoldSplit) + 2 * sizeof(CStage));
     const size_t hdr = desc_bytes + kmax_ints(descs, count) * sizeof(int);     // support maps start at zero
     int *kmax_dev = (int *)((char *)workspace + desc_bytes);

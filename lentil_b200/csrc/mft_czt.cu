@@ -4,49 +4,71 @@
 // D = U' - R' (D depends on u - i only),  R'U' = (R'^2 + U'^2 - D^2) / 2, hence along one axis
 //     y[u] = post[u] * sum_i (pre[i] x[i]) h[u - i],   pre = cis(sgn pi a R'^2), post = cis(sgn pi a U'^2), h = cis(-sgn pi a D^2)
 // (Bluestein / chirp-z).  The convolution runs per row as FFT_L -> x H -> IFFT_L in shared memory, L the power of two
-// >= n_in + n_out - 1 (2048 for the 1001 -> 1024 bench shape), H = FFT_L(h) built once per (plane, axis).
-// One plane of 1001^2 -> 1024^2 is 2025 row transforms ~ 0.5 GFLOP of FP64 instead of the 4.15 GFLOP the folded DMMA
-// kernel executes (16.6 GFLOP algorithmic); exact for any alpha / shift / offset / parity like the other executions.
+// >= n_in + n_out - 1 (2048 for the 1001 -> 1024 bench shape, 8192 for the 4081 -> 2048 planes of BASELINE configs[4]),
+// H = FFT_L(h) built once per (plane, axis).  One plane of 1001^2 -> 1024^2 is 2025 row transforms ~ 0.5 GFLOP of FP64
+// instead of the 4.15 GFLOP the folded DMMA kernel executes (16.6 GFLOP algorithmic); exact for any alpha / shift /
+// offset / parity like the other executions.
 //
 //  * every chirp phase is formed in cycles with error-free products and reduced exactly before sincospi (cis_cycles),
-//    the FFT twiddles come from per-pass tables of exactly reduced sincospi values: parity vs the oracle ~1e-13.
-//  * FFT: Stockham auto-sort in shared memory, radix 8 passes (+ one radix 4 or 2 pass), L/8 threads, one butterfly per
-//    thread and pass, two padded buffers (one 16-byte element of padding per 8: the stride-8 stores of the first pass
-//    are bank-conflict free).
+//    the FFT twiddles come from per-pass tables of exactly reduced sincospi values: parity vs the oracle ~1e-14.
+//  * FFT: Stockham auto-sort in shared memory, RADIX-16 passes, L/16 threads per row, one radix-16 butterfly per thread
+//    and pass: log2 L = 4 a + b  ->  a radix-16 passes and one pass of radix 2^b (b = 1..4) in the middle of the row (the
+//    "turn").  Whatever the radix, thread t owns the elements t + s L/16 (s = 0..15) on the natural-order side of every
+//    pass, so a pass can run in place in ONE buffer (read own 16 -> barrier -> scatter) or ping-pong between two.
 //  * the inverse transform is run as the adjoints of the forward passes in reverse order, so the last forward pass, the
-//    product with H and the first inverse pass of a thread happen in registers (pass_turn); the first forward pass loads
-//    straight from global memory and the last inverse pass stores straight to it (czt_row).
-//  * stage A transforms the rows of f (contiguous loads; K1 can be fused: the phasor amp*mask*exp(2 pi i opd / lambda)
-//    is formed in the load, lentil/plane.py:502-507) and stores its result transposed, stage B transforms the rows of
-//    that (= the columns of the plane) and stores F, or |F|^2 as float64 when the caller only wants intensities.
-//  * L <= 4096 (two buffers of L complex128 must fit in 227 KB of shared memory): larger planes use the folded DMMA
-//    execution (the dispatcher in mft_c128.cu decides).
+//    product with H and the first inverse pass of a thread happen in registers (turn); the first forward pass loads
+//    straight from global memory and the last inverse pass stores straight to it.
+//    L = 2048: 8 shared-memory sweeps per row (4 written, 4 read) where the radix-8 form of round 1 needed 12.
+//  * ROWS rows of a plane are transformed by one CTA, interleaved in the lane index (lane % ROWS = row): twiddles,
+//    chirps and H are loaded once per ROWS rows (same address across those lanes), and the transposed store of stage A /
+//    the column store of stage B write ROWS adjacent elements (32-byte sectors are filled from ROWS = 2 on).
+//    Shared-memory element i of row c lives at (i + i / 16) * ROWS + c: one element of padding per 16 makes the
+//    stride-16 scatter of the first pass conflict-free, every other access of a quarter-warp is contiguous.
+//  * stage A transforms the rows of f (K1 can be fused: the phasor amp*mask*exp(2 pi i opd / lambda) is formed in the
+//    load, lentil/plane.py:502-507) and stores its result transposed, stage B transforms the rows of that (= the
+//    columns of the plane) and stores F, or |F|^2 as float64 when the caller only wants intensities.
+//  * L <= 8192: one buffer of L complex128 (139 KB with padding) is the most that fits the 227 KB of an SM; longer
+//    transforms use the folded DMMA execution (the dispatcher in mft_c128.cu decides).
 #include "lfd_common.cuh"
 #include <mutex>
 
 namespace lfd {
 namespace czt {
 
-constexpr int MAX_LOG2L = 12, MIN_LOG2L = 6;
-// Pass twiddles, one contiguous run per (FFT length, pass): g_tw[lg][(Ns - 1) / 7 + k] = exp(-2 pi i k / (Ns R)) for the pass
-// whose sub-transform length is Ns = 8^p (R = 8, or the 4 / 2 of the last pass), k = 0 .. Ns - 1.  Consecutive butterflies
-// read consecutive entries (a warp: 512 contiguous bytes) instead of gathering from one table of L-th roots.
-constexpr int TW_PER_LEN = 1024;                 // 1 + 8 + 64 + 512 = 585 entries for the longest transform
-__device__ double2 g_tw[MAX_LOG2L + 1][TW_PER_LEN];
+constexpr int MAX_LOG2L = 13, MIN_LOG2L = 6;
+// pass plan of a length: nreg radix-16 passes (the first of them has no twiddles), then the turn of radix 2 / 4 / 8 / 16
+__host__ __device__ constexpr int nreg(int lg) { return (lg - 1) / 4; }
+__host__ __device__ constexpr int turn_radix(int lg) { return 1 << (lg - 4 * nreg(lg)); }
+// Pass twiddles, one contiguous run per (FFT length, pass): pass p >= 1 has sub-transform length Ns = 16^p and reads
+// g_tw[lg][tw_offset(p) + k] = exp(-2 pi i k / (Ns R)), k = 0 .. Ns - 1 (R = 16, or the turn's radix for p = nreg).
+// Consecutive butterflies read consecutive entries.
+__host__ __device__ constexpr int tw_offset(int p) { return ((1 << (4 * p)) - 16) / 15; }
+constexpr int TW_PER_LEN = 4400;                 // 16 + 256 + 4096 = 4368 entries for the longest transform
+__device__ double2 g_tw[MAX_LOG2L - MIN_LOG2L + 1][TW_PER_LEN];
+
+// rows per CTA and buffers per row, by length.  ROWS * L = 4096 elements per CTA (256 threads) up to L = 4096.
+#ifndef LFD_CZT_ELEMS
+#define LFD_CZT_ELEMS 4096
+#endif
+#ifndef LFD_CZT_NBUF
+#define LFD_CZT_NBUF 1
+#endif
+__host__ __device__ constexpr int rows_for(int lg) { return (1 << lg) >= LFD_CZT_ELEMS ? 1 : LFD_CZT_ELEMS >> lg; }
+__host__ __device__ constexpr int nbuf_for(int lg) { return ((size_t)LFD_CZT_NBUF * rows_for(lg) * ((1 << lg) + (1 << lg) / 16) * 16 > 200 * 1024) ? 1 : LFD_CZT_NBUF; }
 
 __global__ void roots_kernel() {
     const int lg = MIN_LOG2L + blockIdx.y;
-    const int npass = lg / 3 + (lg % 3 ? 1 : 0), rlast = lg % 3 == 0 ? 8 : (lg % 3 == 2 ? 4 : 2);
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    int Ns = 1, off = 0;
-    for (int p = 0; p < npass; ++p) {
+    const int np = nreg(lg);
+    for (int p = 1; p <= np; ++p) {
+        const int Ns = 1 << (4 * p), off = tw_offset(p);
         if (e >= off && e < off + Ns) {
-            const int k = e - off, R = (p == npass - 1) ? rlast : 8;
+            const int k = e - off;
+            const double den = p < np ? 16.0 * Ns : (double)(1 << lg);
             double s, c;
-            sincospi(-2.0 * (double)k / (double)(Ns * R), &s, &c);      // k / (Ns R) is exact (power-of-two denominator)
-            g_tw[lg][e] = make_double2(c, s);
+            sincospi(-2.0 * (double)k / den, &s, &c);      // k / den is exact (power-of-two denominator)
+            g_tw[blockIdx.y][e] = make_double2(c, s);
         }
-        off += Ns; Ns *= 8;
     }
 }
 
@@ -66,12 +88,15 @@ struct Plane {
     double wavelength;
 };
 
-__device__ __forceinline__ int P(int i) { return i + (i >> 3); }
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 // multiply by -i (S = +1: forward transform) or by +i (S = -1: inverse)
 template <int S> __device__ __forceinline__ double2 mul_mi(double2 a) { return S > 0 ? make_double2(a.y, -a.x) : make_double2(-a.y, a.x); }
+// multiply by the constant (wr, -S wi): a root of unity of the forward (S = +1) or inverse transform
+template <int S> __device__ __forceinline__ double2 mul_root(double2 a, double wr, double wi) {
+    return S > 0 ? make_double2(a.x * wr + a.y * wi, a.y * wr - a.x * wi) : make_double2(a.x * wr - a.y * wi, a.y * wr + a.x * wi);
+}
 
 template <int S> __device__ __forceinline__ void dft2p(double2 &x0, double2 &x1) {
     const double2 s = cadd(x0, x1), d = csub(x0, x1);
@@ -94,171 +119,146 @@ template <int S> __device__ __forceinline__ void dft8(double2 (&v)[8]) {
     v[0] = a0; v[2] = a1; v[4] = a2; v[6] = a3;
     v[1] = b0; v[3] = b1; v[5] = b2; v[7] = b3;
 }
-
-// Element sources / sinks of a pass: shared memory (padded layout), or the caller's functor (global memory).
-struct SmemIn  { const double2 *p; __device__ __forceinline__ double2 operator()(int i) const { return p[P(i)]; } };
-struct SmemOut { double2 *p; __device__ __forceinline__ void operator()(int i, double2 v) const { p[P(i)] = v; } };
-// twiddle of butterfly j in the pass with sub-transform length Ns (callers fetch it before the barrier that precedes the pass)
-template <int LOG2L> __device__ __forceinline__ double2 pass_twiddle(int j, int Ns) { return g_tw[LOG2L][(Ns - 1) / 7 + (j & (Ns - 1))]; }
-
-template <int R, int S, int LOG2L, class In, class Out>
-__device__ __forceinline__ void pass(const In &in, const Out &out, int j, int Ns, double2 w1 = make_double2(1.0, 0.0)) {
-    constexpr int L = 1 << LOG2L;
-    const int k = j & (Ns - 1);
-    double2 v[R];
+// 16-point DFT, natural order in and out, as 4 x 4: n = 4 n1 + n2, k = k1 + 4 k2,
+//   X[k1 + 4 k2] = sum_n2 w4^(n2 k2) [ w16^(n2 k1) sum_n1 x[4 n1 + n2] w4^(n1 k1) ]
+template <int S> __device__ __forceinline__ void dft16(double2 (&v)[16]) {
+    const double h = 0.70710678118654752440, c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = in(j + r * (L / R));
-    if (Ns > 1) {
-        if (S < 0) w1.y = -w1.y;
-        double2 w = w1;
+    for (int n2 = 0; n2 < 4; ++n2) dft4<S>(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);      // -> y[n2][k1] at v[4 k1 + n2]
+    v[5]  = mul_root<S>(v[5], c1, s1);        // k1 = 1: w16^1, w16^2, w16^3
+    v[6]  = mul_root<S>(v[6], h, h);
+    v[7]  = mul_root<S>(v[7], s1, c1);
+    v[9]  = mul_root<S>(v[9], h, h);          // k1 = 2: w16^2, w16^4, w16^6
+    v[10] = mul_mi<S>(v[10]);
+    v[11] = mul_root<S>(v[11], -h, h);
+    v[13] = mul_root<S>(v[13], s1, c1);       // k1 = 3: w16^3, w16^6, w16^9
+    v[14] = mul_root<S>(v[14], -h, h);
+    v[15] = mul_root<S>(v[15], -c1, -s1);
 #pragma unroll
-        for (int r = 1; r < R; ++r) { v[r] = cmul(v[r], w); if (r + 1 < R) w = cmul(w, w1); }
-    }
-    if constexpr (R == 8) dft8<S>(v);
+    for (int k1 = 0; k1 < 4; ++k1) dft4<S>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);   // X[k1 + 4 k2] at v[4 k1 + k2]
+    // 4 x 4 transpose of the register names
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = a + 1; b < 4; ++b) { const double2 x = v[4 * a + b]; v[4 * a + b] = v[4 * b + a]; v[4 * b + a] = x; }
+}
+template <int R, int S> __device__ __forceinline__ void dftR(double2 (&v)[R]) {
+    if constexpr (R == 16) dft16<S>(v);
+    else if constexpr (R == 8) dft8<S>(v);
     else if constexpr (R == 4) dft4<S>(v[0], v[1], v[2], v[3]);
     else dft2p<S>(v[0], v[1]);
-    const int j0 = (j - k) * R + k;
-#pragma unroll
-    for (int r = 0; r < R; ++r) out(j0 + r * Ns, v[r]);
 }
 
-// all butterflies of one pass that thread t owns (L / 8 threads: one radix-8, two radix-4 or four radix-2 butterflies)
-template <int R, int S, int LOG2L, class In, class Out>
-__device__ __forceinline__ void pass_all(const In &in, const Out &out, int t, int Ns) {
-    constexpr int T = (1 << LOG2L) / 8;
+// v[r] *= w^r (CONJ: conj(w)^r), r = 1 .. R - 1: four interleaved chains of powers, each stepping by w^4
+template <int R, bool CONJ> __device__ __forceinline__ void twiddle_powers(double2 (&v)[R], double2 w1) {
+    if (CONJ) w1.y = -w1.y;
+    v[1] = cmul(v[1], w1);
+    if constexpr (R >= 4) {
+        const double2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+        v[2] = cmul(v[2], w2);
+        v[3] = cmul(v[3], w3);
+        if constexpr (R >= 8) {
+            const double2 w4 = cmul(w2, w2);
+            double2 q0 = w4, q1 = w1, q2 = w2, q3 = w3;
 #pragma unroll
-    for (int q = 0; q < 8 / R; ++q) pass<R, S, LOG2L>(in, out, t + q * T, Ns, pass_twiddle<LOG2L>(t + q * T, Ns));
+            for (int a = 4; a < R; a += 4) {
+                q1 = cmul(q1, w4); q2 = cmul(q2, w4); q3 = cmul(q3, w4);
+                v[a] = cmul(v[a], q0); v[a + 1] = cmul(v[a + 1], q1); v[a + 2] = cmul(v[a + 2], q2); v[a + 3] = cmul(v[a + 3], q3);
+                if (a + 4 < R) q0 = cmul(q0, w4);
+            }
+        }
+    }
 }
 
-// Plain FFT of L elements with L / 8 threads (used for the chirp filter H; the row transforms use czt_row below).  The first
-// pass reads through `first`, the last pass writes through `last` (functors: shared or global memory); the passes in
-// between ping-pong between the padded buffers a and b, starting by WRITING a.  Every pass is followed by a __syncthreads().
-template <int S, int LOG2L, class In, class Out>
-__device__ __forceinline__ void fft(double2 *a, double2 *b, int t, const In &first, const Out &last) {
-    constexpr int N8 = LOG2L / 3, REM = LOG2L % 3, NPASS = N8 + (REM ? 1 : 0);
-    constexpr int RLAST = REM == 0 ? 8 : (REM == 2 ? 4 : 2);
-    static_assert(NPASS >= 2, "at least two passes");
-    int Ns = 1;
-    // first pass: radix 8 from `first` into a
-    pass_all<8, S, LOG2L>(first, SmemOut{a}, t, Ns);
-    __syncthreads();
-    Ns *= 8;
-    double2 *src = a, *dst = b;
+// shared-memory slot of element i (per row; rows are interleaved with stride ROWS)
+template <int ROWS> __device__ __forceinline__ int slot(int i) { return (i + (i >> 4)) * ROWS; }
+
+// last forward pass, product with H and first adjoint pass of one butterfly of the turn, in registers and in place
+template <int LOG2L, int ROWS>
+__device__ __forceinline__ void turn(double2 *X, const double2 *__restrict__ H, int t, int q, double2 w1) {
+    constexpr int L = 1 << LOG2L, T = L / 16, RT = turn_radix(LOG2L), NB = 16 / RT, NS = L / RT;
+    const int j = t + q * T;                     // butterfly index = its twiddle index (j < NS)
+    double2 v[RT];
 #pragma unroll
-    for (int p = 1; p < NPASS - 1; ++p) {
-        pass_all<8, S, LOG2L>(SmemIn{src}, SmemOut{dst}, t, Ns);
+    for (int r = 0; r < RT; ++r) v[r] = X[slot<ROWS>(t + (q + r * NB) * T)];
+    twiddle_powers<RT, false>(v, w1);
+    dftR<RT, 1>(v);
+#pragma unroll
+    for (int r = 0; r < RT; ++r) v[r] = cmul(v[r], H[j + r * NS]);
+    dftR<RT, -1>(v);
+    twiddle_powers<RT, true>(v, w1);
+#pragma unroll
+    for (int r = 0; r < RT; ++r) X[slot<ROWS>(t + (q + r * NB) * T)] = v[r];
+}
+
+// One row (per thread: its 16 elements of one row) of the chirp-z convolution y = IFFT(FFT(x) * H).  `load16(v)` fills
+// v[s] with x[t + s L/16] (global memory), y leaves through `store16(v)` (v[s] = y[t + s L/16]).  X / Y are this
+// thread's row base pointers in the two buffers (the same buffer when NBUF == 1); with two buffers the roles alternate
+// from row to row, so the next row's first scatter never meets this row's last reads.  The twiddle of the next pass is
+// fetched before the barrier that precedes it.
+template <int LOG2L, int ROWS, int NBUF, class Load16, class Store16>
+__device__ __forceinline__ void czt_row(double2 *&X, double2 *&Y, int t, const Load16 &load16, const double2 *__restrict__ H,
+                                        const Store16 &store16) {
+    constexpr int L = 1 << LOG2L, T = L / 16, NREG = nreg(LOG2L), RT = turn_radix(LOG2L), NB = 16 / RT;
+    const double2 *__restrict__ tw = g_tw[LOG2L - MIN_LOG2L];
+    double2 v[16];
+    load16(v);
+    dft16<1>(v);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) X[(17 * t + r) * ROWS] = v[r];          // = slot(16 t + r)
+    int Ns = 16;
+#pragma unroll
+    for (int p = 1; p < NREG; ++p) {
+        const int k = t & (Ns - 1), j0 = (t - k) * 16 + k;
+        const double2 w1 = tw[tw_offset(p) + k];
         __syncthreads();
-        double2 *x = src; src = dst; dst = x;
-        Ns *= 8;
-    }
-    pass_all<RLAST, S, LOG2L>(SmemIn{src}, last, t, Ns);
-    __syncthreads();
-}
-
-// The adjoint of a forward pass: reads where the forward pass writes, takes the conjugate butterfly, multiplies by the
-// conjugate twiddles and writes where the forward pass reads.  The forward passes in reverse order, each replaced by its
-// adjoint, are the conjugate (= unnormalised inverse) transform — and the first of them reads exactly the elements the
-// last forward pass of the same thread produced, so that hand-over needs no trip through shared memory.
-template <int R, int LOG2L, class In, class Out>
-__device__ __forceinline__ void pass_adj(const In &in, const Out &out, int j, int Ns, double2 w1) {
-    constexpr int L = 1 << LOG2L;
-    const int k = j & (Ns - 1);
-    const int j0 = (j - k) * R + k;
-    double2 v[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = in(j0 + r * Ns);
-    if constexpr (R == 8) dft8<-1>(v);
-    else if constexpr (R == 4) dft4<-1>(v[0], v[1], v[2], v[3]);
-    else dft2p<-1>(v[0], v[1]);
-    if (Ns > 1) {
-        w1.y = -w1.y;
-        double2 w = w1;
+        for (int s = 0; s < 16; ++s) v[s] = X[slot<ROWS>(t + s * T)];
+        twiddle_powers<16, false>(v, w1);
+        dft16<1>(v);
+        if (NBUF == 1) __syncthreads();
 #pragma unroll
-        for (int r = 1; r < R; ++r) { v[r] = cmul(v[r], w); if (r + 1 < R) w = cmul(w, w1); }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) out(j + r * (L / R), v[r]);
-}
-
-// last forward pass, product with H and first adjoint pass of one butterfly, in registers and in place in `buf`
-template <int R, int LOG2L>
-__device__ __forceinline__ void pass_turn(double2 *buf, const double2 *__restrict__ H, int j, int Ns, double2 w1) {
-    constexpr int L = 1 << LOG2L;
-    const int k = j & (Ns - 1);
-    const int j0 = (j - k) * R + k;
-    double2 v[R], w[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = buf[P(j + r * (L / R))];
-    w[1] = w1;
-#pragma unroll
-    for (int r = 2; r < R; ++r) w[r] = cmul(w[r - 1], w1);
-#pragma unroll
-    for (int r = 1; r < R; ++r) v[r] = cmul(v[r], w[r]);
-    if constexpr (R == 8) dft8<1>(v);
-    else if constexpr (R == 4) dft4<1>(v[0], v[1], v[2], v[3]);
-    else dft2p<1>(v[0], v[1]);
-#pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = cmul(v[r], H[j0 + r * Ns]);
-    if constexpr (R == 8) dft8<-1>(v);
-    else if constexpr (R == 4) dft4<-1>(v[0], v[1], v[2], v[3]);
-    else dft2p<-1>(v[0], v[1]);
-#pragma unroll
-    for (int r = 1; r < R; ++r) v[r] = cmul(v[r], make_double2(w[r].x, -w[r].y));
-#pragma unroll
-    for (int r = 0; r < R; ++r) buf[P(j + r * (L / R))] = v[r];
-}
-
-// One row of the chirp-z convolution: y = IFFT(FFT(x) * H).  `load8(j, v)` fills v[r] with x[j + r L/8] (global memory,
-// all eight loads issued before any arithmetic), y leaves through `store`.  The twiddle of the next pass is fetched
-// before the barrier that precedes it, so its latency overlaps the barrier wait.
-template <int LOG2L, class Load8, class Out>
-__device__ __forceinline__ void czt_row(double2 *a, double2 *b, int t, const Load8 &load8, const double2 *__restrict__ H, const Out &store) {
-    constexpr int T = (1 << LOG2L) / 8, N8 = LOG2L / 3, REM = LOG2L % 3, NPASS = N8 + (REM ? 1 : 0);
-    constexpr int RLAST = REM == 0 ? 8 : (REM == 2 ? 4 : 2);
-    static_assert(NPASS >= 2, "at least two passes");
-    int Ns = 8;
-    {   // first pass (Ns = 1: no twiddles): global -> registers -> a
-        double2 v[8];
-        load8(t, v);
-        dft8<1>(v);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) a[P(8 * t + r)] = v[r];
-    }
-    double2 *src = a, *dst = b;
-#pragma unroll
-    for (int p = 1; p < NPASS - 1; ++p) {
-        const double2 w1 = pass_twiddle<LOG2L>(t, Ns);
-        __syncthreads();
-        pass<8, 1, LOG2L>(SmemIn{src}, SmemOut{dst}, t, Ns, w1);
-        double2 *x = src; src = dst; dst = x;
-        Ns *= 8;
+        for (int r = 0; r < 16; ++r) Y[slot<ROWS>(j0 + r * Ns)] = v[r];
+        if (NBUF == 2) { double2 *x = X; X = Y; Y = x; }
+        Ns *= 16;
     }
     {
-        double2 wt[8 / RLAST];
+        double2 wt[NB];
 #pragma unroll
-        for (int q = 0; q < 8 / RLAST; ++q) wt[q] = pass_twiddle<LOG2L>(t + q * T, Ns);
+        for (int q = 0; q < NB; ++q) wt[q] = tw[tw_offset(NREG) + t + q * T];
         __syncthreads();
 #pragma unroll
-        for (int q = 0; q < 8 / RLAST; ++q) pass_turn<RLAST, LOG2L>(src, H, t + q * T, Ns, wt[q]);
+        for (int q = 0; q < NB; ++q) turn<LOG2L, ROWS>(X, H, t, q, wt[q]);
     }
 #pragma unroll
-    for (int p = NPASS - 2; p >= 1; --p) {
-        Ns /= 8;
-        const double2 w1 = pass_twiddle<LOG2L>(t, Ns);
+    for (int p = NREG - 1; p >= 1; --p) {
+        Ns /= 16;
+        const int k = t & (Ns - 1), j0 = (t - k) * 16 + k;
+        const double2 w1 = tw[tw_offset(p) + k];
         __syncthreads();
-        pass_adj<8, LOG2L>(SmemIn{src}, SmemOut{dst}, t, Ns, w1);
-        double2 *x = src; src = dst; dst = x;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = X[slot<ROWS>(j0 + r * Ns)];
+        dft16<-1>(v);
+        twiddle_powers<16, true>(v, w1);
+        if (NBUF == 1) __syncthreads();
+#pragma unroll
+        for (int s = 0; s < 16; ++s) Y[slot<ROWS>(t + s * T)] = v[s];
+        if (NBUF == 2) { double2 *x = X; X = Y; Y = x; }
     }
     __syncthreads();
-    pass_adj<8, LOG2L>(SmemIn{src}, store, t, 1, make_double2(1.0, 0.0));
-    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = X[(17 * t + r) * ROWS];
+    dft16<-1>(v);
+    store16(v);
+    if (NBUF == 1) __syncthreads();
+    else { double2 *x = X; X = Y; Y = x; }
 }
 
 // ---- per (plane, axis): pre / post chirps and the transformed chirp filter H = FFT_L(h) -----------------
 template <int LOG2L>
-__global__ void __launch_bounds__((1 << LOG2L) / 8)
+__global__ void __launch_bounds__((1 << LOG2L) / 16)
 czt_tables_kernel(const Plane *__restrict__ descs) {
-    constexpr int L = 1 << LOG2L, T = L / 8;
+    constexpr int L = 1 << LOG2L, T = L / 16, NREG = nreg(LOG2L), RT = turn_radix(LOG2L), NB = 16 / RT, NS = L / RT;
     extern __shared__ double2 sm[];
     const Plane &d = descs[blockIdx.x];
     const bool axisA = blockIdx.y == 0;
@@ -279,113 +279,176 @@ czt_tables_kernel(const Plane *__restrict__ descs) {
         cis_cycles(alpha, v, 0.5 * v, d.sgn, c, s);
         post[u] = make_double2(c * post_scale, s * post_scale);
     }
-    double2 *a = sm, *b = sm + (L + L / 8);
     const double dd = y0 - x0;                       // D = (u - i) + (y0 - x0)
     const double sg = d.sgn;
-    // circular position q holds the lag p = u - i: p = q for q < nout, p = q - L for the negative lags
-    auto chirp = [=](int q) -> double2 {
+    // plain forward FFT of the chirp: circular position q holds the lag p = u - i (p = q for q < nout, p = q - L for the
+    // negative lags); one buffer, in place
+    double2 *X = sm;
+    const double2 *__restrict__ tw = g_tw[LOG2L - MIN_LOG2L];
+    double2 v[16];
+#pragma unroll
+    for (int sI = 0; sI < 16; ++sI) {
+        const int q = t + sI * T;
         const int p = q < nout ? q : q - L;
-        if (p <= -nin || p >= nout) return make_double2(0.0, 0.0);
-        const double D = (double)p + dd;
-        double cc, ss;
-        cis_cycles(alpha, D, 0.5 * D, -sg, cc, ss);
-        return make_double2(cc, ss);
-    };
-    auto to_H = [=](int q, double2 v) { H[q] = v; };
-    fft<1, LOG2L>(a, b, t, chirp, to_H);
+        v[sI] = make_double2(0.0, 0.0);
+        if (p > -nin && p < nout) {
+            const double D = (double)p + dd;
+            double cc, ss;
+            cis_cycles(alpha, D, 0.5 * D, -sg, cc, ss);
+            v[sI] = make_double2(cc, ss);
+        }
+    }
+    dft16<1>(v);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) X[17 * t + r] = v[r];
+    int Ns = 16;
+#pragma unroll
+    for (int p = 1; p < NREG; ++p) {
+        const int k = t & (Ns - 1), j0 = (t - k) * 16 + k;
+        const double2 w1 = tw[tw_offset(p) + k];
+        __syncthreads();
+#pragma unroll
+        for (int sI = 0; sI < 16; ++sI) v[sI] = X[slot<1>(t + sI * T)];
+        twiddle_powers<16, false>(v, w1);
+        dft16<1>(v);
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 16; ++r) X[slot<1>(j0 + r * Ns)] = v[r];
+        Ns *= 16;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+        const int j = t + q * T;
+        double2 u[RT];
+#pragma unroll
+        for (int r = 0; r < RT; ++r) u[r] = X[slot<1>(t + (q + r * NB) * T)];
+        twiddle_powers<RT, false>(u, tw[tw_offset(NREG) + j]);
+        dftR<RT, 1>(u);
+#pragma unroll
+        for (int r = 0; r < RT; ++r) H[j + r * NS] = u[r];
+    }
 }
 
 // ---- one stage: every row of every plane whose FFT length is L ----------------------------------------------
 // STAGE_A: row i of f (n elements, or the fused phasor) -> Gt[:, i] (N outputs, transposed store)
 // else   : row v of Gt (m elements)                     -> out[:, v] (M outputs; complex128 or |.|^2 float64)
-// resident CTAs the register allocation must allow: ~768 threads per SM (3 CTAs of the 2048-point transform)
-constexpr int min_ctas(int log2l) { return (1 << log2l) / 8 >= 768 ? 1 : (768 / ((1 << log2l) / 8) > 16 ? 16 : 768 / ((1 << log2l) / 8)); }
+// A CTA takes ROWS consecutive rows at a time (lane % ROWS = row).  Register budget: 128 per thread (512 threads per SM).
+__host__ __device__ constexpr int cta_threads(int lg) { return ((1 << lg) / 16) * rows_for(lg); }
+__host__ __device__ constexpr int min_ctas(int lg) { return cta_threads(lg) >= 512 ? 1 : 512 / cta_threads(lg); }
 
 template <int LOG2L, bool STAGE_A>
-__global__ void __launch_bounds__((1 << LOG2L) / 8, min_ctas(LOG2L))
-czt_stage_kernel(const Plane *__restrict__ descs, int count, int max_rows) {
-    constexpr int L = 1 << LOG2L, T = L / 8;
+__global__ void __launch_bounds__(cta_threads(LOG2L), min_ctas(LOG2L))
+czt_stage_kernel(const Plane *__restrict__ descs, int count, int max_groups) {
+    constexpr int L = 1 << LOG2L, T = L / 16, ROWS = rows_for(LOG2L), NBUF = nbuf_for(LOG2L), NT = T * ROWS;
     extern __shared__ double2 sm[];
-    double2 *a = sm, *b = sm + (L + L / 8);
-    const int t = threadIdx.x;
-    const long long total = (long long)count * max_rows;
+    const int c = threadIdx.x % ROWS, t = threadIdx.x / ROWS;
+    double2 *X = sm + c, *Y = sm + (NBUF - 1) * ROWS * (L + L / 16) + c;
+    const long long total = (long long)count * max_groups;
     __shared__ Plane sd;                 // the plane this CTA is working on (rows are dealt plane-major: it changes rarely)
     int cur = -1;
     for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-        const int plane = (int)(w / max_rows);
-        const int row = (int)(w - (long long)plane * max_rows);
+        const int plane = (int)(w / max_groups);
+        const int row0 = (int)(w - (long long)plane * max_groups) * ROWS;
         if (plane != cur) {              // uniform over the CTA
             __syncthreads();
             const unsigned long long *g = reinterpret_cast<const unsigned long long *>(descs + plane);
             unsigned long long *sdw = reinterpret_cast<unsigned long long *>(&sd);
-            for (int i = t; i < (int)(sizeof(Plane) / 8); i += T) sdw[i] = g[i];
+            for (int i = threadIdx.x; i < (int)(sizeof(Plane) / 8); i += NT) sdw[i] = g[i];
             __syncthreads();
             cur = plane;
         }
         const Plane &d = sd;
         const int nrows = STAGE_A ? d.m : d.N;
-        if (row >= nrows || (STAGE_A ? d.logLA : d.logLB) != LOG2L) continue;     // uniform over the CTA
+        if (row0 >= nrows || (STAGE_A ? d.logLA : d.logLB) != LOG2L) continue;     // uniform over the CTA
+        const int row = row0 + c;
+        const bool rv = row < nrows;
         const int nin = STAGE_A ? d.n : d.m, nout = STAGE_A ? d.N : d.M;
         const double2 *__restrict__ pre = STAGE_A ? d.preA : d.preB;
         const double2 *__restrict__ post = STAGE_A ? d.postA : d.postB;
         const double2 *__restrict__ H = STAGE_A ? d.HA : d.HB;
         const Plane *dp = &d;
-        // first forward pass: the eight inputs of this thread straight from global memory (x pre-chirp; zero beyond the
-        // input length), every load issued before the arithmetic
-        auto load = [=](int j, double2 (&v)[8]) {
-            double2 pr[8];
-            if (STAGE_A && dp->amp != nullptr) {
-                double am[8], op[8];
-                const long long base = (long long)(dp->pr0 + row) * dp->pld + dp->pc0;
-                const unsigned char *mk = dp->mask;
+        // first forward pass: the inputs of this thread straight from global memory (x pre-chirp; zero beyond the input
+        // length), in two halves of eight so that every load of a half is issued before its arithmetic
+        auto load = [=](double2 (&v)[16]) {
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const int i = j + r * (L / 8);
-                    const bool in = i < nin;
-                    am[r] = in ? dp->amp[base + i] : 0.0;
-                    op[r] = in ? dp->opd[base + i] : 0.0;
-                    pr[r] = in ? pre[i] : make_double2(0.0, 0.0);
-                    if (in && mk != nullptr && mk[base + i] == 0) am[r] = 0.0;
+            for (int hf = 0; hf < 2; ++hf) {
+                if (hf * 8 * T >= nin) {                                 // uniform: this half lies beyond the input
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) v[hf * 8 + s] = make_double2(0.0, 0.0);
+                    continue;
                 }
-                const double lam = dp->wavelength;
+                double2 pr[8];
+                if (STAGE_A && dp->amp != nullptr) {
+                    double am[8], op[8];
+                    const long long base = (long long)(dp->pr0 + row) * dp->pld + dp->pc0;
+                    const unsigned char *mk = dp->mask;
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    double2 x = make_double2(0.0, 0.0);
-                    if (am[r] != 0.0) {                        // same arithmetic as K1 (pupil_prep.cu): phase in cycles, reduced exactly
-                        const double tcyc = op[r] / lam;
-                        double sn, cs;
-                        sincospi(2.0 * (tcyc - rint(tcyc)), &sn, &cs);
-                        x = make_double2(am[r] * cs, am[r] * sn);
+                    for (int s = 0; s < 8; ++s) {
+                        const int i = t + (hf * 8 + s) * T;
+                        const bool in = rv && i < nin;
+                        am[s] = in ? dp->amp[base + i] : 0.0;
+                        op[s] = in ? dp->opd[base + i] : 0.0;
+                        pr[s] = in ? pre[i] : make_double2(0.0, 0.0);
+                        if (in && mk != nullptr && mk[base + i] == 0) am[s] = 0.0;
                     }
-                    v[r] = cmul(x, pr[r]);
-                }
-            } else {
-                const double2 *src = STAGE_A ? dp->f + (long long)row * dp->ldf : dp->Gt + (long long)row * dp->mpad;
+                    const double lam = dp->wavelength;
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const int i = j + r * (L / 8);
-                    const bool in = i < nin;
-                    v[r] = in ? src[i] : make_double2(0.0, 0.0);
-                    pr[r] = in ? pre[i] : make_double2(0.0, 0.0);
-                }
+                    for (int s = 0; s < 8; ++s) {
+                        double2 x = make_double2(0.0, 0.0);
+                        if (am[s] != 0.0) {                        // same arithmetic as K1 (pupil_prep.cu): phase in cycles, reduced exactly
+                            const double tcyc = op[s] / lam;
+                            double sn, cs;
+                            sincospi(2.0 * (tcyc - rint(tcyc)), &sn, &cs);
+                            x = make_double2(am[s] * cs, am[s] * sn);
+                        }
+                        v[hf * 8 + s] = cmul(x, pr[s]);
+                    }
+                } else {
+                    const double2 *src = STAGE_A ? dp->f + (long long)row * dp->ldf : dp->Gt + (long long)row * dp->mpad;
+                    double2 x[8];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) v[r] = cmul(v[r], pr[r]);
+                    for (int s = 0; s < 8; ++s) {
+                        const int i = t + (hf * 8 + s) * T;
+                        const bool in = rv && i < nin;
+                        x[s] = in ? src[i] : make_double2(0.0, 0.0);
+                        pr[s] = in ? pre[i] : make_double2(0.0, 0.0);
+                    }
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) v[hf * 8 + s] = cmul(x[s], pr[s]);
+                }
             }
         };
         if (STAGE_A) {
             double2 *Gt = dp->Gt; const long long mpad = dp->mpad;
-            auto store = [=](int i, double2 v) { if (i < nout) Gt[(long long)i * mpad + row] = cmul(v, post[i]); };
-            czt_row<LOG2L>(a, b, t, load, H, store);
+            auto store = [=](double2 (&v)[16]) {
+#pragma unroll
+                for (int s = 0; s < 16; ++s) {
+                    const int i = t + s * T;
+                    if (rv && i < nout) Gt[(long long)i * mpad + row] = cmul(v[s], post[i]);
+                }
+            };
+            czt_row<LOG2L, ROWS, NBUF>(X, Y, t, load, H, store);
         } else if (dp->intensity) {
             double *out = (double *)dp->out; const long long ldo = dp->ldo;
-            auto store = [=](int i, double2 v) {
-                if (i < nout) { const double2 z = cmul(v, post[i]); out[(long long)i * ldo + row] = z.x * z.x + z.y * z.y; }
+            auto store = [=](double2 (&v)[16]) {
+#pragma unroll
+                for (int s = 0; s < 16; ++s) {
+                    const int i = t + s * T;
+                    if (rv && i < nout) { const double2 z = cmul(v[s], post[i]); out[(long long)i * ldo + row] = z.x * z.x + z.y * z.y; }
+                }
             };
-            czt_row<LOG2L>(a, b, t, load, H, store);
+            czt_row<LOG2L, ROWS, NBUF>(X, Y, t, load, H, store);
         } else {
             double2 *out = (double2 *)dp->out; const long long ldo = dp->ldo;
-            auto store = [=](int i, double2 v) { if (i < nout) out[(long long)i * ldo + row] = cmul(v, post[i]); };
-            czt_row<LOG2L>(a, b, t, load, H, store);
+            auto store = [=](double2 (&v)[16]) {
+#pragma unroll
+                for (int s = 0; s < 16; ++s) {
+                    const int i = t + s * T;
+                    if (rv && i < nout) out[(long long)i * ldo + row] = cmul(v[s], post[i]);
+                }
+            };
+            czt_row<LOG2L, ROWS, NBUF>(X, Y, t, load, H, store);
         }
     }
 }
@@ -393,9 +456,10 @@ czt_stage_kernel(const Plane *__restrict__ descs, int count, int max_rows) {
 static inline size_t al(size_t v) { return (v + 255) / 256 * 256; }
 static inline int log2_len(int nin, int nout) {
     int lg = MIN_LOG2L;
-    while ((1 << lg) < nin + nout - 1) ++lg;
+    while ((1LL << lg) < (long long)nin + nout - 1) ++lg;
     return lg;
 }
+static inline int pad_rows(int m) { return (m + 7) & ~7; }
 
 }  // namespace czt
 
@@ -408,17 +472,14 @@ bool czt_supported(const lfd_mft_desc *descs, int count) {
     return true;
 }
 
-// LFD_MFT_AUTO: chirp-z wherever it can run.  Measured against the folded DMMA form on dense random planes, batched
-// (scripts/small_plane_timing.py, r01o): 121^2 -> 128^2 0.66 vs 0.73 us, 241^2 -> 256^2 2.9 vs 3.1 us, 501^2 -> 512^2 12.4 vs
-// 19.3 us, 1001^2 -> 1024^2 53.6 vs 139 us, 2001^2 -> 2048^2 251 vs 1036 us per plane; cfg3's 900 windows 9.5 vs 12.6 ms.
+// LFD_MFT_AUTO: chirp-z wherever it can run (measured against the folded DMMA form: DESIGN.md section 4).
 bool czt_preferred(const lfd_mft_desc *descs, int count) { return czt_supported(descs, count); }
 
 size_t czt_workspace_bytes(const lfd_mft_desc *descs, int count) {
     size_t bytes = al((size_t)count * sizeof(Plane));
     for (int i = 0; i < count; ++i) {
         const lfd_mft_desc &p = descs[i];
-        const int mpad = (p.m + 1) & ~1;
-        bytes += al((size_t)p.N * mpad * sizeof(double2));
+        bytes += al((size_t)p.N * pad_rows(p.m) * sizeof(double2));
         bytes += al(((size_t)p.n + p.N + ((size_t)1 << log2_len(p.n, p.N))) * sizeof(double2));
         bytes += al(((size_t)p.m + p.M + ((size_t)1 << log2_len(p.m, p.M))) * sizeof(double2));
     }
@@ -427,36 +488,35 @@ size_t czt_workspace_bytes(const lfd_mft_desc *descs, int count) {
 
 template <int LOG2L>
 static int launch_for_length(const Plane *dd, int count, int max_rows_a, int max_rows_b, bool any_a, bool any_b,
-                             int phase, int nsm, cudaStream_t stream) {
-    constexpr int L = 1 << LOG2L, T = L / 8;
-    const int smem = 2 * (L + L / 8) * (int)sizeof(double2);
-    static bool attr_set = false;
-    if (!attr_set) {
-        LFD_CUDA_OK(cudaFuncSetAttribute(czt_tables_kernel<LOG2L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        LFD_CUDA_OK(cudaFuncSetAttribute(czt_stage_kernel<LOG2L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        LFD_CUDA_OK(cudaFuncSetAttribute(czt_stage_kernel<LOG2L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+                             int phase, int dev, int nsm, cudaStream_t stream) {
+    constexpr int L = 1 << LOG2L, ROWS = rows_for(LOG2L), NBUF = nbuf_for(LOG2L), NT = cta_threads(LOG2L);
+    const int smem_tab = (L + L / 16) * (int)sizeof(double2);
+    const int smem = NBUF * ROWS * smem_tab;
     if (phase == 0) {
-        czt_tables_kernel<LOG2L><<<dim3(count, 2), T, smem, stream>>>(dd);
+        if (ensure_dynamic_smem(dev, (const void *)czt_tables_kernel<LOG2L>, smem_tab)) return 1;
+        czt_tables_kernel<LOG2L><<<dim3(count, 2), L / 16, smem_tab, stream>>>(dd);
         LFD_CUDA_OK(cudaGetLastError());
         count_launch();
         return 0;
     }
     int occ = 1;
     if (phase == 1 && any_a) {
-        LFD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, czt_stage_kernel<LOG2L, true>, T, smem));
-        const long long total = (long long)count * max_rows_a;
+        if (ensure_dynamic_smem(dev, (const void *)czt_stage_kernel<LOG2L, true>, smem)) return 1;
+        LFD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, czt_stage_kernel<LOG2L, true>, NT, smem));
+        const int groups = (max_rows_a + ROWS - 1) / ROWS;
+        const long long total = (long long)count * groups;
         const int grid = (int)(total < (long long)nsm * occ ? total : (long long)nsm * occ);
-        czt_stage_kernel<LOG2L, true><<<grid, T, smem, stream>>>(dd, count, max_rows_a);
+        czt_stage_kernel<LOG2L, true><<<grid, NT, smem, stream>>>(dd, count, groups);
         LFD_CUDA_OK(cudaGetLastError());
         count_launch();
     }
     if (phase == 2 && any_b) {
-        LFD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, czt_stage_kernel<LOG2L, false>, T, smem));
-        const long long total = (long long)count * max_rows_b;
+        if (ensure_dynamic_smem(dev, (const void *)czt_stage_kernel<LOG2L, false>, smem)) return 1;
+        LFD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, czt_stage_kernel<LOG2L, false>, NT, smem));
+        const int groups = (max_rows_b + ROWS - 1) / ROWS;
+        const long long total = (long long)count * groups;
         const int grid = (int)(total < (long long)nsm * occ ? total : (long long)nsm * occ);
-        czt_stage_kernel<LOG2L, false><<<grid, T, smem, stream>>>(dd, count, max_rows_b);
+        czt_stage_kernel<LOG2L, false><<<grid, NT, smem, stream>>>(dd, count, groups);
         LFD_CUDA_OK(cudaGetLastError());
         count_launch();
     }
@@ -473,17 +533,18 @@ int launch_mft_czt(const lfd_mft_desc *descs, int count, void *workspace, size_t
 
     int dev = 0, nsm = 0;
     LFD_CUDA_OK(cudaGetDevice(&dev));
-    LFD_CUDA_OK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    nsm = sm_count(dev);
+    LFD_REQUIRE(nsm > 0, "lfd_mft_c128 (chirp-z): cannot query device %d", dev);
     {   // FFT roots: once per device and process
         static std::mutex mu;
         static bool ready[64] = {false};
         std::lock_guard<std::mutex> lock(mu);
-        if (dev < 64 && !ready[dev]) {
-            roots_kernel<<<dim3(TW_PER_LEN / 256, MAX_LOG2L - MIN_LOG2L + 1), 256, 0, stream>>>();
+        if (dev >= 64 || !ready[dev]) {
+            roots_kernel<<<dim3((TW_PER_LEN + 255) / 256, MAX_LOG2L - MIN_LOG2L + 1), 256, 0, stream>>>();
             LFD_CUDA_OK(cudaGetLastError());
             LFD_CUDA_OK(cudaStreamSynchronize(stream));
             count_launch();
-            ready[dev] = true;
+            if (dev < 64) ready[dev] = true;
         }
     }
 
@@ -505,7 +566,7 @@ int launch_mft_czt(const lfd_mft_desc *descs, int count, void *workspace, size_t
         }
         Plane &d = h[i];
         d.f = (const double2 *)p.f; d.ldf = p.ldf; d.out = p.out; d.ldo = p.ldo;
-        d.m = p.m; d.n = p.n; d.M = p.M; d.N = p.N; d.mpad = (p.m + 1) & ~1;
+        d.m = p.m; d.n = p.n; d.M = p.M; d.N = p.N; d.mpad = pad_rows(p.m);
         d.logLA = log2_len(p.n, p.N); d.logLB = log2_len(p.m, p.M); d.intensity = intensity_out;
         d.Gt = (double2 *)(ws + off); off += al((size_t)p.N * d.mpad * sizeof(double2));
         const size_t LA = (size_t)1 << d.logLA, LB = (size_t)1 << d.logLB;
@@ -536,8 +597,9 @@ int launch_mft_czt(const lfd_mft_desc *descs, int count, void *workspace, size_t
             if (!(useA[lg] || useB[lg])) continue;
             int rc = 0;
             switch (lg) {
-#define LFD_CZT_CASE(LG) case LG: rc = launch_for_length<LG>(dd, count, max_m, max_N, useA[LG], useB[LG], phase, nsm, stream); break;
+#define LFD_CZT_CASE(LG) case LG: rc = launch_for_length<LG>(dd, count, max_m, max_N, useA[LG], useB[LG], phase, dev, nsm, stream); break;
                 LFD_CZT_CASE(6) LFD_CZT_CASE(7) LFD_CZT_CASE(8) LFD_CZT_CASE(9) LFD_CZT_CASE(10) LFD_CZT_CASE(11) LFD_CZT_CASE(12)
+                LFD_CZT_CASE(13)
 #undef LFD_CZT_CASE
             default: break;
             }

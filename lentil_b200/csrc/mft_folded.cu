@@ -55,7 +55,6 @@ constexpr int FTHREADS = 128;  // 4 warps stacked along the rows, each 16 folded
                                // prologue / epilogue hides under the other's MMAs
 constexpr int FRESEED_TILES = 64;  // re-seed the twiddle recurrence every 1024 folded K (2048 input rows)
 constexpr int FOLD_MAX_TILES = 1024;  // folded-column tiles per plane the support map can hold (inputs up to 32768 columns)
-constexpr int FIRST_WAVE_SMS = 148;  // B200: CTAs with linear id < 2*148 form the first wave
 constexpr int FBLOCK_ELEMS = 2 * FBK * FBC;                      // complex elements per (column tile, K tile) block
 constexpr unsigned FBLOCK_BYTES = FBLOCK_ELEMS * sizeof(double2);   // 16 KB
 constexpr size_t FSMEM_BYTES = (size_t)FSTAGES * FBLOCK_BYTES;
@@ -249,7 +248,9 @@ mft_folded_kernel(const FStageDesc *__restrict__ descs) {
     // Two CTAs share an SM and every tile of a batch takes the same time, so left alone they run in
     // lockstep and their prologues/epilogues (no MMAs) coincide.  The second CTA to arrive on an SM
     // in the first wave waits half a tile once; the offset then persists for the whole launch.
-    if (blockIdx.y * gridDim.x + blockIdx.x < 2 * FIRST_WAVE_SMS) {
+    unsigned nsm;                                // CTAs with linear id < 2 * (SMs of this device) form the first wave
+    asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+    if (blockIdx.y * gridDim.x + blockIdx.x < 2 * nsm) {
         __shared__ unsigned s_slot;
         if (threadIdx.x == 0) {
             unsigned smid;
@@ -535,14 +536,10 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
     LFD_REQUIRE(workspace_bytes >= need, "lfd_mft_c128_batched: workspace too small (%zu < %zu)",
                 workspace_bytes, need);
     LFD_REQUIRE(count <= 32767, "lfd_mft_c128_batched: at most 32767 planes per call (got %d)", count);
-    static bool attr_set = false;
-    if (!attr_set) {
-        LFD_CUDA_OK(cudaFuncSetAttribute(mft_folded_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)FSMEM_BYTES));
-        LFD_CUDA_OK(cudaFuncSetAttribute(mft_folded_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)FSMEM_BYTES));
-        attr_set = true;
-    }
+    int dev = 0;
+    LFD_CUDA_OK(cudaGetDevice(&dev));
+    if (ensure_dynamic_smem(dev, (const void *)mft_folded_kernel<true>, (int)FSMEM_BYTES)) return 1;
+    if (ensure_dynamic_smem(dev, (const void *)mft_folded_kernel<false>, (int)FSMEM_BYTES)) return 1;
     const size_t desc_bytes = (size_t)count * (sizeof(FoldDesc) + 2 * sizeof(FStageDesc));
     size_t kmax_ints = 0;
     for (int i = 0; i < count; ++i) kmax_ints += 2 * (((descs[i].n + 1) / 2 + FBC / 2 - 1) / (FBC / 2));

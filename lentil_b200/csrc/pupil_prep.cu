@@ -90,7 +90,7 @@ static int pupil_prep_impl(bool c64, const double *amp, const double *opd, const
             }
             for (int l = 0; l < P.nlam; ++l) P.lam[l] = wavelengths[l0 + l];
             long long bx = (max_elem + 255) / 256;
-            if (bx > 148 * 16) bx = 148 * 16;  // grid-stride beyond 16 CTAs per SM
+            if (bx > sm_or_default() * 16) bx = sm_or_default() * 16;  // grid-stride beyond 16 CTAs per SM
             dim3 grid((unsigned)bx, (unsigned)P.nseg);
             if (c64)
                 pupil_prep_kernel<float2><<<grid, 256, 0, stream>>>(amp, opd, mask, n_r, n_c, P,

@@ -192,7 +192,7 @@ rescale_finish_kernel(const double *__restrict__ re, const double *__restrict__ 
 
 static inline unsigned spl_grid(long long n) {
     long long b = (n + 255) / 256;
-    return (unsigned)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b));
+    return (unsigned)(b > sm_or_default() * 16 ? sm_or_default() * 16 : (b < 1 ? 1 : b));
 }
 
 static int spline_poles(int order, double *z) {

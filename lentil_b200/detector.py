@@ -17,20 +17,28 @@ def _to_dev(img):
 
 
 def rebin(img, factor):
-    """Rebin an image (or a cube of images along axis 0) by an integer factor; trailing rows/columns
-    that do not fill a block are dropped, as numpy's reshape in the reference requires exact division."""
+    """Rebin an image (or a cube of images along axis 0) by an integer factor (lentil/util.py:206-258).
+    Like the reference (whose numpy reshape needs exact division) a shape that `factor` does not divide is a
+    ValueError; host input keeps its dtype on the way out, device tensors come back as float64."""
     if np.iscomplexobj(img) if not device.is_dev(img) else img.is_complex():
         raise ValueError('rebin is not defined for complex data')
+    in_dtype = None if device.is_dev(img) else np.asarray(img).dtype
     d, on_dev = _to_dev(img)
     planes = d.reshape((-1,) + tuple(d.shape[-2:]))
     h, w = int(planes.shape[1]), int(planes.shape[2])
+    if h % int(factor) or w % int(factor):
+        raise ValueError(f'cannot reshape array of size {h * w} into shape '
+                         f'({h // factor},{factor},{w // factor},{factor})')
     out = device.zeros_f64(planes.shape[0], h // factor, w // factor)
     L = _lib.lib()
     for k in range(planes.shape[0]):
         _lib.check(L.lfd_rebin(planes[k].data_ptr(), device.ld_of(planes[k]), h, w, int(factor), out[k].data_ptr(),
                                device.stream_ptr()), "lfd_rebin")
     out = out.reshape(tuple(d.shape[:-2]) + (h // factor, w // factor))
-    return out if on_dev else device.to_host(out)
+    if on_dev:
+        return out
+    res = device.to_host(out)
+    return res if in_dtype is None or in_dtype == res.dtype else res.astype(in_dtype)
 
 
 def pixel(img, oversample=1):
@@ -215,7 +223,8 @@ def rescale(img, scale, shape=None, mask=None, order=3, mode='nearest', unitary=
     x = (np.arange(shape[1], dtype=np.float64) - shape[1] / 2.) / scale + w / 2.
     y = (np.arange(shape[0], dtype=np.float64) - shape[0] / 2.) / scale + h / 2.
 
-    planes = [d.real.contiguous(), d.imag.contiguous()] if is_complex else [d if d.dtype == torch.float64 else d.double()]
+    # dense planes: the sums below (lfd_sum_f64) read numel() consecutive doubles, so a strided view must be packed first
+    planes = [d.real.contiguous(), d.imag.contiguous()] if is_complex else [d.double().contiguous()]
     if mask is None:
         # mask = (img != 0) interpolated bilinearly (util.py:315-319, 334); for complex data a pixel is non-zero when
         # either part is: form |re| + |im| once, the kernel reads it as a 0/1 map

@@ -196,6 +196,10 @@ def accumulate_intensity(fields, out_dev, groups=None, weights=None):
     return out_dev
 
 
+# bench.py sets this to a list to get (start event, end event, algorithmic bytes) per K3 launch
+TIMERS = None
+
+
 def accumulate_windows(wins, out_dev):
     """K3 on a prepared numpy table of lfd_window rows (dtype np.dtype(_lib.Window))."""
     n = len(wins)
@@ -203,10 +207,18 @@ def accumulate_windows(wins, out_dev):
         return out_dev
     H, W = int(out_dev.shape[0]), int(out_dev.shape[1])
     scratch = device.empty_bytes(C.sizeof(_lib.Window) * n)
+    if TIMERS is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = _lib.lib().lfd_accum_intensity(wins.ctypes.data_as(C.POINTER(_lib.Window)), n, out_dev.data_ptr(),
                                         H, W, device.ld_of(out_dev), scratch.data_ptr(), scratch.numel(),
                                         device.stream_ptr())
     _lib.check(rc, "lfd_accum_intensity")
+    if TIMERS is not None:
+        e1.record()
+        esize = np.where(wins['c64'] == 2, 8, np.where(wins['c64'] == 1, 8, 16))     # float64 intensity / complex64 / complex128
+        TIMERS.append((e0, e1, float(np.sum(wins['h'].astype(np.int64) * wins['w'] * esize) + 16.0 * H * W)))
     return out_dev
 
 

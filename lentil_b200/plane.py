@@ -244,13 +244,13 @@ class Plane(_PlaneBase):
                 raise ValueError('array amplitude/opd need a 2-D (or 3-D segment) mask')
         ops = {'nseg': nseg, 'shape': shape, 'pshape': () if full else shape, 'scalar': None}
         use_mask = amp.size != 1 and not derived   # plane.py:503 — a scalar amplitude is not masked
-        mk_dev = None
+        mk_dev, mask_binary = None, True
         if mask is not None:
             mk = mask.reshape((nseg,) + shape)
             if mk.dtype == bool:
                 mk8 = mk.view(np.uint8)
             else:
-                binary = np.all((mk == 0) | (mk == 1))
+                binary = mask_binary = bool(np.all((mk == 0) | (mk == 1)))
                 if not binary and use_mask:
                     if nseg > 1:
                         raise NotImplementedError('non-binary segment masks are not supported')
@@ -260,6 +260,9 @@ class Plane(_PlaneBase):
         ops['amp'] = device.to_dev(amp if amp.shape == shape else np.broadcast_to(amp, shape), dtype=np.float64)
         ops['opd'] = device.to_dev(opd if opd.shape == shape else np.broadcast_to(opd, shape), dtype=np.float64)
         ops['mask'] = mk_dev if use_mask else None
+        # the uploaded 0/1 mask cube itself, whether or not the phasor needs it (a scalar amplitude is not masked, but
+        # fit_tilt still fits over the mask: lentil/plane.py:522-562)
+        ops['mask_dev'], ops['mask_binary'] = mk_dev, mask_binary
         # bounding boxes on the device
         if full:
             bb = np.array([[0, shape[0] - 1, 0, shape[1] - 1]])
@@ -393,11 +396,13 @@ class Plane(_PlaneBase):
         ops = plane._operands()
         if ops['scalar'] is not None:
             return plane
-        if ops['mask'] is None and not (plane._mask is None and type(plane).__mask__ is _PlaneBase.__mask__):
+        if not ops['mask_binary']:
             raise NotImplementedError('fit_tilt with a non-binary mask is not supported')
         nseg, (n_r, n_c) = ops['nseg'], ops['shape']
         L = _lib.lib()
-        mask_ptr = ops['mask'].data_ptr() if ops['mask'] is not None else None
+        # an explicit mask is the fit's support even when the phasor ignores it (scalar amplitude); a derived mask is
+        # amplitude != 0, which the kernels evaluate themselves
+        mask_ptr = ops['mask_dev'].data_ptr() if ops['mask_dev'] is not None else None
         moments = device.zeros_f64(nseg * 9)
         scratch = device.empty_bytes(64 * nseg)
         _lib.check(L.lfd_fit_tilt_moments(ops['opd'].data_ptr(), mask_ptr, ops['amp'].data_ptr(), n_r, n_c,

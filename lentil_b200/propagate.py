@@ -269,7 +269,9 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
     if opds is None:
         R, opd_stack = 1, None
     else:
-        opd_stack = opds if device.is_dev(opds) else device.to_dev(np.asarray(opds), dtype=np.float64)
+        # the kernels read the stack as dense float64 on this device: normalise whatever the caller handed over
+        opd_stack = (opds.to(device.device(), torch.float64).contiguous() if device.is_dev(opds)
+                     else device.to_dev(np.asarray(opds), dtype=np.float64))
         if opd_stack.dim() != 3 or tuple(opd_stack.shape[1:]) != tuple(ops['shape']):
             raise ValueError(f"opds must have shape (R, {ops['shape'][0]}, {ops['shape'][1]})")
         R = int(opd_stack.shape[0])
@@ -285,7 +287,15 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
     z = getattr(plane, 'focal_length', None)
 
     my = shard_indices(L, distributed)
-    stack = out if out is not None else device.zeros_f64(R * P, H, W)
+    if out is not None:
+        if not (device.is_dev(out) and out.dtype == torch.float64 and out.device == device.device()
+                and out.is_contiguous() and out.numel() == R * P * H * W):
+            raise ValueError(f'out must be a contiguous float64 tensor on {device.device()} with {R * P * H * W} '
+                             f'elements ([R,] [P,] {H}, {W})')
+    # a distributed call all-reduces what THIS call computed and only then adds it to `out` (whose previous contents
+    # would otherwise be summed once per rank)
+    reduce_into = out if (out is not None and distributed) else None
+    stack = out if (out is not None and reduce_into is None) else device.zeros_f64(R * P, H, W)
     stack3 = stack.view(R * P, H, W)
 
     nseg = ops['nseg']
@@ -408,6 +418,9 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
 
     if distributed:
         reduce_stack(stack)
+    if reduce_into is not None:
+        reduce_into.view(R * P, H, W).add_(stack3)
+        stack3 = reduce_into.view(R * P, H, W)
     result = stack3.view(R, P, H, W)
     if tilts is None:
         result = result[:, 0]

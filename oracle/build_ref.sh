@@ -1,0 +1,35 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE — stages the real reference (andykee/lentil, pure Python) under oracle/_ref/ so that it travels to
+# the GPU box with the snapshot (oracle/_ref/ is git-ignored: reference sources never enter this repository's history).
+#
+# Used only as the checker / CPU baseline:
+#   * bench.py --impl reference and bench.py's cpu_baseline leg time it on the host cores (kind: "reference"),
+#   * tests/ import it to test lentil_b200.patch.enable() against the real package and to cross-check the oracle port.
+# Nothing under lentil_b200/ imports it.
+#
+# The copy is pinned: every file's sha256 must match oracle/ref_manifest.sha256 (written once with --pin from the
+# reference tree this work was developed against, lentil 0.8.8).  Runs only where /root/reference exists (the build
+# container); on the GPU box the already-staged copy is used as is.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+SRC="${LENTIL_REFERENCE:-/root/reference}"
+DST="$HERE/_ref"
+MANIFEST="$HERE/ref_manifest.sha256"
+
+if [ ! -d "$SRC/lentil" ]; then
+    if [ -d "$DST/lentil" ]; then echo "oracle/_ref: reference tree absent, keeping the staged copy"; exit 0; fi
+    echo "oracle/_ref: no reference tree at $SRC and nothing staged" >&2; exit 1
+fi
+if [ "${1:-}" = "--pin" ]; then
+    (cd "$SRC" && find lentil -name '*.py' -type f | LC_ALL=C sort | xargs sha256sum) > "$MANIFEST"
+    echo "pinned $(wc -l < "$MANIFEST") files"
+fi
+(cd "$SRC" && sha256sum --quiet -c "$MANIFEST")
+rm -rf "$DST"
+mkdir -p "$DST/lentil"
+(cd "$SRC" && find lentil -name '*.py' -type f | LC_ALL=C sort) | while read -r f; do
+    mkdir -p "$DST/$(dirname "$f")"
+    cp "$SRC/$f" "$DST/$f"
+done
+(cd "$DST" && sha256sum --quiet -c "$MANIFEST")
+echo "oracle/_ref: staged $(wc -l < "$MANIFEST") files of lentil $(grep -o "__version__ = .*" "$DST/lentil/__init__.py" | head -1)"

@@ -56,7 +56,7 @@ TOL64 = 1e-10
 
 @pytest.fixture(params=["folded", "direct", "czt", "auto"])
 def mft_variant(request):
-    """Run a test under both executions of K2a (LFD_MFT_AUTO is the default: chirp-z up to 4096-point transforms, else
+    """Run a test under both executions of K2a (LFD_MFT_AUTO is the default: chirp-z up to 8192-point transforms, else
     the folded DMMA form; LFD_MFT_DIRECT is the plain complex x complex form); restores the default afterwards."""
     from lentil_b200 import _lib
     L = _lib.lib()

@@ -226,7 +226,7 @@ def test_sparse_support_patterns(kind):
 
 
 def test_chirpz_length_boundaries_and_fallback():
-    # the chirp-z execution pads each axis to the power of two >= n_in + n_out - 1 (64 .. 4096); beyond 4096 the library runs
+    # the chirp-z execution pads each axis to the power of two >= n_in + n_out - 1 (64 .. 8192); beyond 8192 the library runs
     # the folded DMMA form instead.  Rectangular planes keep the long axis cheap.
     L = _lib.lib()
     rng = np.random.default_rng(41)
@@ -236,7 +236,9 @@ def test_chirpz_length_boundaries_and_fallback():
         for (m, n), (M, N), expect in [((33, 32), (32, 33), 2),        # 64 exactly on both axes
                                        ((32, 5), (34, 7), 2),          # 65 -> 128, 11 -> 64
                                        ((2049, 8), (2048, 8), 2),      # 4096 exactly
-                                       ((2100, 8), (2048, 8), 1)]:     # 4147 > 4096: folded
+                                       ((2100, 8), (2048, 8), 2),      # 4147 -> 8192 (one buffer, in place)
+                                       ((8, 4097), (8, 4096), 2),      # 8192 exactly, on the column axis
+                                       ((4200, 8), (4096, 8), 1)]:     # 8295 > 8192: folded
             d = (_lib.MftDesc * 1)()
             d[0].m, d[0].n, d[0].M, d[0].N = m, n, M, N
             assert L.lfd_mft_execution(d, 1) == expect, (m, n, M, N)

@@ -354,20 +354,21 @@ def test_k2a_execution_choice_and_workspace_are_host_decisions():
 
     try:
         bench_plane = descs((1001, 1001, 1024, 1024))
-        cfg5_plane = descs((4081, 4081, 2048, 2048))          # 6128 -> 8192-point transform: too long for shared memory
-        mixed = descs((241, 241, 256, 256), (4081, 4081, 2048, 2048))
+        cfg5_plane = descs((4081, 4081, 2048, 2048))          # 6128 -> 8192-point transform: the longest that fits shared memory
+        huge = descs((6000, 16, 4096, 16))                    # 10095 -> 16384 points: folded DMMA form
+        mixed = descs((241, 241, 256, 256), (6000, 16, 4096, 16))
         tiny = descs((7, 5, 4, 9))
         assert L.lfd_get_mft_variant() == 3                    # LFD_MFT_AUTO is the default
-        for variant, expect in ((0, (0, 0, 0, 0)), (1, (1, 1, 1, 1)), (2, (2, 1, 1, 2)), (3, (2, 1, 1, 2))):
+        for variant, expect in ((0, (0, 0, 0, 0, 0)), (1, (1, 1, 1, 1, 1)), (2, (2, 2, 1, 1, 2)), (3, (2, 2, 1, 1, 2))):
             assert L.lfd_set_mft_variant(variant) == 0
-            got = tuple(L.lfd_mft_execution(*b) for b in (bench_plane, cfg5_plane, mixed, tiny))
+            got = tuple(L.lfd_mft_execution(*b) for b in (bench_plane, cfg5_plane, huge, mixed, tiny))
             assert got == expect, (variant, got)
-            for b in (bench_plane, cfg5_plane, mixed, tiny):
+            for b in (bench_plane, cfg5_plane, huge, mixed, tiny):
                 assert L.lfd_mft_workspace_bytes(*b) > 0
         # the chirp-z workspace holds the transposed intermediate (N x m complex128) plus three tables per axis
         L.lfd_set_mft_variant(2)
         need = L.lfd_mft_workspace_bytes(*bench_plane)
-        assert 1024 * 1002 * 16 <= need <= 1024 * 1002 * 16 + (1 << 20)
+        assert 1024 * 1008 * 16 <= need <= 1024 * 1008 * 16 + (1 << 20)
         assert L.lfd_set_mft_variant(7) != 0 and b"unknown MFT variant" in L.lfd_last_error()
     finally:
         L.lfd_set_mft_variant(saved)
