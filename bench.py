@@ -378,19 +378,17 @@ def run_ours(args):
     probe_desc[0].m = probe_desc[0].n = 2 * w["radius"] + 1          # bounding box of the pupil
     probe_desc[0].M = probe_desc[0].N = w["det"] * w["oversample"]
     execution = {0: "direct", 1: "folded", 2: "czt"}[lib.lfd_mft_execution(probe_desc, 1)]
-    configured = lib.lfd_get_mft_variant()
     dmma = None
     if execution != "folded":
-        lib.lfd_set_mft_variant(1)
         for _ in range(3):
-            psf_d = step_resident()
+            psf_d = step_resident(execution="folded")          # per-call choice (lfd_mft_desc.execution), no process-wide switch
         barrier()
         fourier.TIMERS = []
         d0, d1 = _event_pair(torch)
         d0.record()
         nd = min(steps, 10)
         for _ in range(nd):
-            psf_d = step_resident()
+            psf_d = step_resident(execution="folded")
         d1.record()
         barrier()
         d_mft_ms = sum(t_[0].elapsed_time(t_[1]) for t_ in fourier.TIMERS)
@@ -398,7 +396,6 @@ def run_ours(args):
         d_alg = sum(t_[2] for t_ in fourier.TIMERS)
         d_launches = len(fourier.TIMERS)
         fourier.TIMERS = None
-        lib.lfd_set_mft_variant(configured)
         d_ms, = _max_over_ranks(torch, dist, dev, [d0.elapsed_time(d1)])
         dmma = {"value": w["nlam"] * world * nd / (d_ms * 1e-3), "unit": "planes/s", "steps": nd,
                 "avg_launch_ms": d_mft_ms / max(d_launches, 1), "launches": d_launches,
@@ -536,7 +533,7 @@ def run_ours(args):
         roofline_tensor.update({
             "bound": "tensor", "peak": probe["dmma_tflops"], "unit": "TFLOP/s",
             "frac": dmma["achieved"] / probe["dmma_tflops"],
-            "kernel": "mft_folded_kernel<true>+<false> (FP64 DMMA.8x8x4, forced with lfd_set_mft_variant(LFD_MFT_FOLDED))",
+            "kernel": "mft_folded_kernel<true>+<false> (FP64 DMMA.8x8x4, forced per call with lfd_mft_desc.execution = 1 + LFD_MFT_FOLDED)",
             "note": "the north star's FP64 tensor-core execution on the same workload: achieved = EXECUTED DMMA flops "
                     "(two real x complex GEMMs of ceil(M/2) x ceil(K/2) per stage; an upper bound, the row stage skips K tiles "
                     "its support map marks empty) / launch time; frac = % of the measured FP64 tensor-core (DMMA) issue peak. "

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define LFD_ABI_VERSION 1
+#define LFD_ABI_VERSION 2
 
 /* ---- errors / introspection ------------------------------------------------------------ */
 int         lfd_abi_version(void);
@@ -58,20 +58,26 @@ typedef struct lfd_mft_desc {
     double      off_r, off_c;       /* input-plane offset (pixels)                     */
     int32_t     unitary;            /* fourier.py:100-101                              */
     int32_t     inverse;            /* 0: dft2, 1: idft2 semantics                     */
+    int32_t     execution;          /* 0: the process default (lfd_set_mft_variant); 1 + LFD_MFT_x: run this batch with
+                                       execution x whatever the default is.  Read from the FIRST descriptor of a batch
+                                       (one launch = one execution); per-call, so concurrent threads / streams can
+                                       choose independently                                                   */
+    int32_t     reserved_;          /* must be 0                                       */
 } lfd_mft_desc;
 
 /* Three executions of the same transform (results agree to rounding):
  *   LFD_MFT_DIRECT : complex twiddle x complex data, 4 real DMMAs per complex 8x8x4 block
  *   LFD_MFT_FOLDED : even/odd folding of both axes -> real twiddles, 4x fewer DMMAs (default)
  *   LFD_MFT_CZT    : chirp-z (Bluestein) execution on the FP64 pipe: per row FFT_L -> x FFT(chirp) -> IFFT_L in shared
- *                    memory, ~8x fewer flops than the folded form; planes whose FFT length would exceed 4096
- *                    (n_in + n_out - 1 > 4096 on an axis) are run by the folded execution instead
- * Process-wide switch; affects lfd_mft_workspace_bytes and the lfd_mft_* launches that follow. */
+ *                    memory, ~8x fewer flops than the folded form; planes whose FFT length would exceed 8192
+ *                    (n_in + n_out - 1 > 8192 on an axis) are run by the folded execution instead
+ * lfd_set_mft_variant sets the process-wide DEFAULT (affects lfd_mft_workspace_bytes and the lfd_mft_* launches that
+ * follow, for descriptors whose `execution` field is 0); lfd_mft_desc.execution overrides it per call. */
 #define LFD_MFT_DIRECT 0
 #define LFD_MFT_FOLDED 1
 #define LFD_MFT_CZT    2
-#define LFD_MFT_AUTO   3   /* default: chirp-z whenever every plane of the batch fits it (FFT length <= 4096 on both axes;
-                            * measured faster than the folded form at every size from 128^2 to 2048^2), else folded */
+#define LFD_MFT_AUTO   3   /* default: chirp-z whenever every plane of the batch fits it (FFT length <= 8192 on both axes;
+                            * measured faster than the folded form at every size from 128^2 up), else folded */
 int lfd_set_mft_variant(int variant);
 int lfd_get_mft_variant(void);
 /* which execution (LFD_MFT_DIRECT / FOLDED / CZT) a batch runs under the current setting */

@@ -27,6 +27,7 @@ class MftDesc(C.Structure):
         ("shift_r", C.c_double), ("shift_c", C.c_double),
         ("off_r", C.c_double), ("off_c", C.c_double),
         ("unitary", C.c_int32), ("inverse", C.c_int32),
+        ("execution", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -127,7 +128,7 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.lfd_abi_version() != 1:
+        if handle.lfd_abi_version() != 2:
             raise LfdError("liblentil_b200.so ABI version mismatch")
         for which, struct in enumerate((MftDesc, Segment, Window)):
             if handle.lfd_struct_size(which) != C.sizeof(struct):

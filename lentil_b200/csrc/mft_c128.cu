@@ -196,7 +196,9 @@ static std::atomic<int> g_variant{LFD_MFT_AUTO};
 
 // the execution a batch runs under the current process-wide setting
 int mft_resolve_execution(const lfd_mft_desc *descs, int count) {
-    const int v = g_variant.load();
+    // per-call choice (lfd_mft_desc.execution of the first plane) before the process default
+    const int forced = (descs && count > 0) ? descs[0].execution : 0;
+    const int v = (forced >= 1 && forced <= 1 + LFD_MFT_AUTO) ? forced - 1 : g_variant.load();
     if (v == LFD_MFT_CZT) return czt_supported(descs, count) ? LFD_MFT_CZT : LFD_MFT_FOLDED;
     if (v == LFD_MFT_AUTO) return czt_preferred(descs, count) ? LFD_MFT_CZT : LFD_MFT_FOLDED;
     return v;

@@ -46,14 +46,33 @@ __host__ __device__ constexpr int tw_offset(int p) { return ((1 << (4 * p)) - 16
 constexpr int TW_PER_LEN = 4400;                 // 16 + 256 + 4096 = 4368 entries for the longest transform
 __device__ double2 g_tw[MAX_LOG2L - MIN_LOG2L + 1][TW_PER_LEN];
 
-// rows per CTA and buffers per row, by length.  ROWS * L = 4096 elements per CTA (256 threads) up to L = 4096.
+// rows per CTA and buffers per row, by length (measured, r02: profiles/r02_czt_variants.md): 128-thread CTAs up to
+// L = 1024 (ROWS * L = 2048), two rows (256 threads) at L = 2048, one row beyond.  LFD_CZT_ELEMS overrides ROWS * L.
 #ifndef LFD_CZT_ELEMS
-#define LFD_CZT_ELEMS 4096
+#define LFD_CZT_ELEMS 0
 #endif
 #ifndef LFD_CZT_NBUF
 #define LFD_CZT_NBUF 1
 #endif
-__host__ __device__ constexpr int rows_for(int lg) { return (1 << lg) >= LFD_CZT_ELEMS ? 1 : LFD_CZT_ELEMS >> lg; }
+// tables fetched before the barrier that precedes their pass (registers are free there, but only so many of them)
+#ifndef LFD_CZT_HPRE
+#define LFD_CZT_HPRE 8        // how many of a thread's 16 values of H are fetched before the turn's barrier (0, 4, 8 or 16)
+#endif
+#ifndef LFD_CZT_PRE_MAXLG
+#define LFD_CZT_PRE_MAXLG 11  // ... all three prefetches only for transforms up to this length: beyond it (radix-16 turn, 512-thread
+#endif                        // CTAs) they cost registers or L2 bandwidth and measured 3 % slower (r02, profiles/r02_czt_variants.md)
+#ifndef LFD_CZT_L2PRE
+#define LFD_CZT_L2PRE 1       // prefetch.global.L2 of the next unit's input rows
+#endif
+#ifndef LFD_CZT_CONTIG
+#define LFD_CZT_CONTIG 0      // 1: one contiguous run of work units per CTA instead of the round-robin deal (see czt_stage_kernel)
+#endif
+#ifndef LFD_CZT_PPRE
+#define LFD_CZT_PPRE 4        // post-chirp factors prefetched before the last pass (0 .. 8)
+#endif
+__host__ __device__ constexpr int rows_for(int lg) {
+    return LFD_CZT_ELEMS ? ((1 << lg) >= LFD_CZT_ELEMS ? 1 : LFD_CZT_ELEMS >> lg) : (lg <= 10 ? 2048 >> lg : (lg == 11 ? 2 : 1));
+}
 __host__ __device__ constexpr int nbuf_for(int lg) { return ((size_t)LFD_CZT_NBUF * rows_for(lg) * ((1 << lg) + (1 << lg) / 16) * 16 > 200 * 1024) ? 1 : LFD_CZT_NBUF; }
 
 __global__ void roots_kernel() {
@@ -173,18 +192,18 @@ template <int R, bool CONJ> __device__ __forceinline__ void twiddle_powers(doubl
 // shared-memory slot of element i (per row; rows are interleaved with stride ROWS)
 template <int ROWS> __device__ __forceinline__ int slot(int i) { return (i + (i >> 4)) * ROWS; }
 
-// last forward pass, product with H and first adjoint pass of one butterfly of the turn, in registers and in place
+// last forward pass, product with H and first adjoint pass of one butterfly of the turn, in registers and in place;
+// hv[r] = H[j + r L/RT] for this butterfly (j = t + q L/16), fetched by the caller before the barrier
 template <int LOG2L, int ROWS>
-__device__ __forceinline__ void turn(double2 *X, const double2 *__restrict__ H, int t, int q, double2 w1) {
-    constexpr int L = 1 << LOG2L, T = L / 16, RT = turn_radix(LOG2L), NB = 16 / RT, NS = L / RT;
-    const int j = t + q * T;                     // butterfly index = its twiddle index (j < NS)
+__device__ __forceinline__ void turn(double2 *X, const double2 *hv, int t, int q, double2 w1) {
+    constexpr int L = 1 << LOG2L, T = L / 16, RT = turn_radix(LOG2L), NB = 16 / RT;
     double2 v[RT];
 #pragma unroll
     for (int r = 0; r < RT; ++r) v[r] = X[slot<ROWS>(t + (q + r * NB) * T)];
     twiddle_powers<RT, false>(v, w1);
     dftR<RT, 1>(v);
 #pragma unroll
-    for (int r = 0; r < RT; ++r) v[r] = cmul(v[r], H[j + r * NS]);
+    for (int r = 0; r < RT; ++r) v[r] = cmul(v[r], hv[r]);
     dftR<RT, -1>(v);
     twiddle_powers<RT, true>(v, w1);
 #pragma unroll
@@ -194,12 +213,14 @@ __device__ __forceinline__ void turn(double2 *X, const double2 *__restrict__ H, 
 // One row (per thread: its 16 elements of one row) of the chirp-z convolution y = IFFT(FFT(x) * H).  `load16(v)` fills
 // v[s] with x[t + s L/16] (global memory), y leaves through `store16(v)` (v[s] = y[t + s L/16]).  X / Y are this
 // thread's row base pointers in the two buffers (the same buffer when NBUF == 1); with two buffers the roles alternate
-// from row to row, so the next row's first scatter never meets this row's last reads.  The twiddle of the next pass is
-// fetched before the barrier that precedes it.
+// from row to row, so the next row's first scatter never meets this row's last reads.  Everything a pass needs from
+// global memory — its twiddle, the 16 values of H for the turn, the first eight post-chirp factors for the last pass — is
+// fetched BEFORE the barrier that precedes the pass: the data registers are dead there (the row lives in shared memory),
+// and the load latency overlaps the barrier wait instead of the arithmetic.
 template <int LOG2L, int ROWS, int NBUF, class Load16, class Store16>
 __device__ __forceinline__ void czt_row(double2 *&X, double2 *&Y, int t, const Load16 &load16, const double2 *__restrict__ H,
-                                        const Store16 &store16) {
-    constexpr int L = 1 << LOG2L, T = L / 16, NREG = nreg(LOG2L), RT = turn_radix(LOG2L), NB = 16 / RT;
+                                        const double2 *__restrict__ post, int nout, const Store16 &store16) {
+    constexpr int L = 1 << LOG2L, T = L / 16, NREG = nreg(LOG2L), RT = turn_radix(LOG2L), NB = 16 / RT, NS = L / RT;
     const double2 *__restrict__ tw = g_tw[LOG2L - MIN_LOG2L];
     double2 v[16];
     load16(v);
@@ -223,12 +244,21 @@ __device__ __forceinline__ void czt_row(double2 *&X, double2 *&Y, int t, const L
         Ns *= 16;
     }
     {
-        double2 wt[NB];
+        // the first HN of this thread's 16 values of H before the barrier, the others once the turn is under way
+        constexpr int HN = LOG2L <= LFD_CZT_PRE_MAXLG ? LFD_CZT_HPRE : 0;
+        double2 wt[NB], hv[16];
 #pragma unroll
         for (int q = 0; q < NB; ++q) wt[q] = tw[tw_offset(NREG) + t + q * T];
+#pragma unroll
+        for (int e = 0; e < HN; ++e) hv[e] = H[t + (e / RT) * T + (e % RT) * NS];
         __syncthreads();
 #pragma unroll
-        for (int q = 0; q < NB; ++q) turn<LOG2L, ROWS>(X, H, t, q, wt[q]);
+        for (int q = 0; q < NB; ++q) {
+#pragma unroll
+            for (int r = 0; r < RT; ++r)
+                if (q * RT + r >= HN) hv[q * RT + r] = H[t + q * T + r * NS];
+            turn<LOG2L, ROWS>(X, hv + q * RT, t, q, wt[q]);
+        }
     }
 #pragma unroll
     for (int p = NREG - 1; p >= 1; --p) {
@@ -245,10 +275,22 @@ __device__ __forceinline__ void czt_row(double2 *&X, double2 *&Y, int t, const L
         for (int s = 0; s < 16; ++s) Y[slot<ROWS>(t + s * T)] = v[s];
         if (NBUF == 2) { double2 *x = X; X = Y; Y = x; }
     }
+    constexpr int PP = LOG2L <= LFD_CZT_PRE_MAXLG ? LFD_CZT_PPRE : 0;   // post-chirp factors fetched before the barrier (outputs t + s L/16, s < PP)
+    double2 pv[PP > 0 ? PP : 1];
+#pragma unroll
+    for (int sI = 0; sI < PP; ++sI) pv[sI] = (t + sI * T < nout) ? post[t + sI * T] : make_double2(0.0, 0.0);
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = X[(17 * t + r) * ROWS];
     dft16<-1>(v);
+#pragma unroll
+    for (int sI = 0; sI < PP; ++sI) v[sI] = cmul(v[sI], pv[sI]);
+#pragma unroll
+    for (int sI = PP; sI < 8; ++sI) v[sI] = (t + sI * T < nout) ? cmul(v[sI], post[t + sI * T]) : v[sI];
+    if (8 * T < nout) {                                    // uniform; outputs beyond half the transform length are rare
+#pragma unroll
+        for (int sI = 8; sI < 16; ++sI) v[sI] = (t + sI * T < nout) ? cmul(v[sI], post[t + sI * T]) : v[sI];
+    }
     store16(v);
     if (NBUF == 1) __syncthreads();
     else { double2 *x = X; X = Y; Y = x; }
@@ -337,19 +379,38 @@ czt_tables_kernel(const Plane *__restrict__ descs) {
 __host__ __device__ constexpr int cta_threads(int lg) { return ((1 << lg) / 16) * rows_for(lg); }
 __host__ __device__ constexpr int min_ctas(int lg) { return cta_threads(lg) >= 512 ? 1 : 512 / cta_threads(lg); }
 
+// Work units (ROWS rows of one plane) are numbered plane-major over the planes of THIS length; starts[p] = units in planes
+// < p (count + 1 entries).  Units are dealt round-robin: at any moment the CTAs of the grid work on ADJACENT rows, so the
+// 16-byte pieces they scatter into the transposed intermediate (stage A) or the output columns (stage B) complete their
+// 128-byte lines in L2 within one unit time.  (A contiguous run of units per CTA keeps a plane's tables in L1 but leaves
+// N x CTAs partially written lines in flight — 77 MB for 2048-point planes — which L2 evicts half filled: measured
+// 1.6x slower at 2001^2 -> 2048^2, LFD_CZT_CONTIG=1.)
 template <int LOG2L, bool STAGE_A>
 __global__ void __launch_bounds__(cta_threads(LOG2L), min_ctas(LOG2L))
-czt_stage_kernel(const Plane *__restrict__ descs, int count, int max_groups) {
+czt_stage_kernel(const Plane *__restrict__ descs, const int *__restrict__ starts, int count) {
     constexpr int L = 1 << LOG2L, T = L / 16, ROWS = rows_for(LOG2L), NBUF = nbuf_for(LOG2L), NT = T * ROWS;
     extern __shared__ double2 sm[];
     const int c = threadIdx.x % ROWS, t = threadIdx.x / ROWS;
     double2 *X = sm + c, *Y = sm + (NBUF - 1) * ROWS * (L + L / 16) + c;
-    const long long total = (long long)count * max_groups;
-    __shared__ Plane sd;                 // the plane this CTA is working on (rows are dealt plane-major: it changes rarely)
-    int cur = -1;
-    for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-        const int plane = (int)(w / max_groups);
-        const int row0 = (int)(w - (long long)plane * max_groups) * ROWS;
+    const int total = starts[count];
+#if LFD_CZT_CONTIG
+    const int per = (total + (int)gridDim.x - 1) / (int)gridDim.x, stride = 1;
+    const int w0 = (int)blockIdx.x * per, w1 = min(total, w0 + per);
+#else
+    const int stride = (int)gridDim.x, w0 = (int)blockIdx.x, w1 = total;
+#endif
+    if (w0 >= w1) return;
+    __shared__ Plane sd;                 // the plane this CTA is working on
+    int plane = 0, cur = -1;
+    {   // last plane whose first unit is <= w0 (planes of another length own no units: their start equals the next one's)
+        int lo = 0, hi = count;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (starts[mid] <= w0) lo = mid; else hi = mid; }
+        plane = lo;
+    }
+    int pbeg = starts[plane], pend = starts[plane + 1];
+    for (int w = w0; w < w1; w += stride) {
+        while (w >= pend) { ++plane; pbeg = pend; pend = starts[plane + 1]; }
+        const int row0 = (w - pbeg) * ROWS;
         if (plane != cur) {              // uniform over the CTA
             __syncthreads();
             const unsigned long long *g = reinterpret_cast<const unsigned long long *>(descs + plane);
@@ -360,7 +421,6 @@ czt_stage_kernel(const Plane *__restrict__ descs, int count, int max_groups) {
         }
         const Plane &d = sd;
         const int nrows = STAGE_A ? d.m : d.N;
-        if (row0 >= nrows || (STAGE_A ? d.logLA : d.logLB) != LOG2L) continue;     // uniform over the CTA
         const int row = row0 + c;
         const bool rv = row < nrows;
         const int nin = STAGE_A ? d.n : d.m, nout = STAGE_A ? d.N : d.M;
@@ -368,6 +428,23 @@ czt_stage_kernel(const Plane *__restrict__ descs, int count, int max_groups) {
         const double2 *__restrict__ post = STAGE_A ? d.postA : d.postB;
         const double2 *__restrict__ H = STAGE_A ? d.HA : d.HB;
         const Plane *dp = &d;
+        if (LFD_CZT_L2PRE && LOG2L <= LFD_CZT_PRE_MAXLG && w + stride < w1 && w + stride < pend && row + stride * ROWS < nrows) {   // next unit in the same plane: pull its input rows into L2 now
+            const long long nrow = row + stride * ROWS;
+#pragma unroll
+            for (int sI = 0; sI < 16; sI += 2) {                         // one prefetch per 32-byte sector pair of this thread's elements
+                const int i = t + sI * T;
+                if (i < nin) {
+                    if (STAGE_A && dp->amp != nullptr) {
+                        const long long e = (nrow + dp->pr0) * dp->pld + dp->pc0 + i;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(dp->amp + e));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(dp->opd + e));
+                    } else {
+                        const double2 *nsrc = STAGE_A ? dp->f + nrow * dp->ldf : dp->Gt + nrow * dp->mpad;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + i));
+                    }
+                }
+            }
+        }
         // first forward pass: the inputs of this thread straight from global memory (x pre-chirp; zero beyond the input
         // length), in two halves of eight so that every load of a half is issued before its arithmetic
         auto load = [=](double2 (&v)[16]) {
@@ -425,30 +502,30 @@ czt_stage_kernel(const Plane *__restrict__ descs, int count, int max_groups) {
 #pragma unroll
                 for (int s = 0; s < 16; ++s) {
                     const int i = t + s * T;
-                    if (rv && i < nout) Gt[(long long)i * mpad + row] = cmul(v[s], post[i]);
+                    if (rv && i < nout) Gt[(long long)i * mpad + row] = v[s];
                 }
             };
-            czt_row<LOG2L, ROWS, NBUF>(X, Y, t, load, H, store);
+            czt_row<LOG2L, ROWS, NBUF>(X, Y, t, load, H, post, nout, store);
         } else if (dp->intensity) {
             double *out = (double *)dp->out; const long long ldo = dp->ldo;
             auto store = [=](double2 (&v)[16]) {
 #pragma unroll
                 for (int s = 0; s < 16; ++s) {
                     const int i = t + s * T;
-                    if (rv && i < nout) { const double2 z = cmul(v[s], post[i]); out[(long long)i * ldo + row] = z.x * z.x + z.y * z.y; }
+                    if (rv && i < nout) out[(long long)i * ldo + row] = v[s].x * v[s].x + v[s].y * v[s].y;
                 }
             };
-            czt_row<LOG2L, ROWS, NBUF>(X, Y, t, load, H, store);
+            czt_row<LOG2L, ROWS, NBUF>(X, Y, t, load, H, post, nout, store);
         } else {
             double2 *out = (double2 *)dp->out; const long long ldo = dp->ldo;
             auto store = [=](double2 (&v)[16]) {
 #pragma unroll
                 for (int s = 0; s < 16; ++s) {
                     const int i = t + s * T;
-                    if (rv && i < nout) out[(long long)i * ldo + row] = cmul(v[s], post[i]);
+                    if (rv && i < nout) out[(long long)i * ldo + row] = v[s];
                 }
             };
-            czt_row<LOG2L, ROWS, NBUF>(X, Y, t, load, H, store);
+            czt_row<LOG2L, ROWS, NBUF>(X, Y, t, load, H, post, nout, store);
         }
     }
 }
@@ -460,6 +537,13 @@ static inline int log2_len(int nin, int nout) {
     return lg;
 }
 static inline int pad_rows(int m) { return (m + 7) & ~7; }
+static inline int rows_for_length(int lg) { return rows_for(lg); }
+constexpr int NLEN = MAX_LOG2L - MIN_LOG2L + 1;
+// workspace header: the plane descriptors, then per (stage, length) the unit start table of count + 1 ints
+static inline size_t header_bytes(int count) { return al((size_t)count * sizeof(Plane) + (size_t)2 * NLEN * (count + 1) * sizeof(int)); }
+static inline size_t starts_offset(int count, int stage, int lg) {
+    return (size_t)count * sizeof(Plane) + ((size_t)stage * NLEN + (lg - MIN_LOG2L)) * (count + 1) * sizeof(int);
+}
 
 }  // namespace czt
 
@@ -476,7 +560,7 @@ bool czt_supported(const lfd_mft_desc *descs, int count) {
 bool czt_preferred(const lfd_mft_desc *descs, int count) { return czt_supported(descs, count); }
 
 size_t czt_workspace_bytes(const lfd_mft_desc *descs, int count) {
-    size_t bytes = al((size_t)count * sizeof(Plane));
+    size_t bytes = header_bytes(count);
     for (int i = 0; i < count; ++i) {
         const lfd_mft_desc &p = descs[i];
         bytes += al((size_t)p.N * pad_rows(p.m) * sizeof(double2));
@@ -487,7 +571,7 @@ size_t czt_workspace_bytes(const lfd_mft_desc *descs, int count) {
 }
 
 template <int LOG2L>
-static int launch_for_length(const Plane *dd, int count, int max_rows_a, int max_rows_b, bool any_a, bool any_b,
+static int launch_for_length(const Plane *dd, int count, const int *starts_a, int total_a, const int *starts_b, int total_b,
                              int phase, int dev, int nsm, cudaStream_t stream) {
     constexpr int L = 1 << LOG2L, ROWS = rows_for(LOG2L), NBUF = nbuf_for(LOG2L), NT = cta_threads(LOG2L);
     const int smem_tab = (L + L / 16) * (int)sizeof(double2);
@@ -500,26 +584,23 @@ static int launch_for_length(const Plane *dd, int count, int max_rows_a, int max
         return 0;
     }
     int occ = 1;
-    if (phase == 1 && any_a) {
+    if (phase == 1 && total_a > 0) {
         if (ensure_dynamic_smem(dev, (const void *)czt_stage_kernel<LOG2L, true>, smem)) return 1;
         LFD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, czt_stage_kernel<LOG2L, true>, NT, smem));
-        const int groups = (max_rows_a + ROWS - 1) / ROWS;
-        const long long total = (long long)count * groups;
-        const int grid = (int)(total < (long long)nsm * occ ? total : (long long)nsm * occ);
-        czt_stage_kernel<LOG2L, true><<<grid, NT, smem, stream>>>(dd, count, groups);
+        const int grid = total_a < nsm * occ ? total_a : nsm * occ;
+        czt_stage_kernel<LOG2L, true><<<grid, NT, smem, stream>>>(dd, starts_a, count);
         LFD_CUDA_OK(cudaGetLastError());
         count_launch();
     }
-    if (phase == 2 && any_b) {
+    if (phase == 2 && total_b > 0) {
         if (ensure_dynamic_smem(dev, (const void *)czt_stage_kernel<LOG2L, false>, smem)) return 1;
         LFD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, czt_stage_kernel<LOG2L, false>, NT, smem));
-        const int groups = (max_rows_b + ROWS - 1) / ROWS;
-        const long long total = (long long)count * groups;
-        const int grid = (int)(total < (long long)nsm * occ ? total : (long long)nsm * occ);
-        czt_stage_kernel<LOG2L, false><<<grid, NT, smem, stream>>>(dd, count, groups);
+        const int grid = total_b < nsm * occ ? total_b : nsm * occ;
+        czt_stage_kernel<LOG2L, false><<<grid, NT, smem, stream>>>(dd, starts_b, count);
         LFD_CUDA_OK(cudaGetLastError());
         count_launch();
     }
+    (void)ROWS;
     return 0;
 }
 
@@ -548,12 +629,14 @@ int launch_mft_czt(const lfd_mft_desc *descs, int count, void *workspace, size_t
         }
     }
 
-    Plane *h = (Plane *)calloc(count, sizeof(Plane));
-    LFD_REQUIRE(h != nullptr, "out of host memory");
+    const size_t hdr = header_bytes(count);
+    char *hbuf = (char *)calloc(hdr, 1);
+    LFD_REQUIRE(hbuf != nullptr, "out of host memory");
+    Plane *h = (Plane *)hbuf;
     char *ws = (char *)workspace;
-    size_t off = al((size_t)count * sizeof(Plane));
+    size_t off = hdr;
     bool useA[MAX_LOG2L + 1] = {false}, useB[MAX_LOG2L + 1] = {false};
-    int max_m = 0, max_N = 0;
+    long long unitsA[MAX_LOG2L + 1] = {0}, unitsB[MAX_LOG2L + 1] = {0};
     for (int i = 0; i < count; ++i) {
         const lfd_mft_desc &p = descs[i];
         const bool ok = p.m > 0 && p.n > 0 && p.M > 0 && p.N > 0 && p.ldo >= p.N && p.out &&
@@ -561,7 +644,7 @@ int launch_mft_czt(const lfd_mft_desc *descs, int count, void *workspace, size_t
                                 src[i].r0 + p.m <= src[i].n_r && src[i].c0 + p.n <= src[i].n_c)
                              : (p.f && p.ldf >= p.n));
         if (!ok) {
-            free(h);
+            free(hbuf);
             LFD_REQUIRE(false, "lfd_mft_c128 (chirp-z): plane %d has invalid shape/ld/pointers", i);
         }
         Plane &d = h[i];
@@ -585,11 +668,27 @@ int launch_mft_czt(const lfd_mft_desc *descs, int count, void *workspace, size_t
             d.pld = src[i].n_c; d.pr0 = src[i].r0; d.pc0 = src[i].c0; d.wavelength = src[i].wavelength;
         }
         useA[d.logLA] = true; useB[d.logLB] = true;
-        if (p.m > max_m) max_m = p.m;
-        if (p.N > max_N) max_N = p.N;
+        // unit start tables: stage A deals the m input rows of the plane, stage B the N columns, ROWS at a time
+        for (int lg = MIN_LOG2L; lg <= MAX_LOG2L; ++lg) {
+            int *sa = (int *)(hbuf + starts_offset(count, 0, lg)), *sb = (int *)(hbuf + starts_offset(count, 1, lg));
+            sa[i] = (int)unitsA[lg]; sb[i] = (int)unitsB[lg];
+        }
+        const int ra = rows_for_length(d.logLA), rb = rows_for_length(d.logLB);
+        unitsA[d.logLA] += (p.m + ra - 1) / ra;
+        unitsB[d.logLB] += (p.N + rb - 1) / rb;
     }
-    cudaError_t e = cudaMemcpyAsync(workspace, h, (size_t)count * sizeof(Plane), cudaMemcpyHostToDevice, stream);
-    free(h);
+    bool too_many = false;
+    for (int lg = MIN_LOG2L; lg <= MAX_LOG2L; ++lg) {
+        ((int *)(hbuf + starts_offset(count, 0, lg)))[count] = (int)unitsA[lg];
+        ((int *)(hbuf + starts_offset(count, 1, lg)))[count] = (int)unitsB[lg];
+        too_many |= unitsA[lg] > 0x7fffffffLL || unitsB[lg] > 0x7fffffffLL;
+    }
+    if (too_many) {
+        free(hbuf);
+        LFD_REQUIRE(false, "lfd_mft_c128 (chirp-z): too many rows in one batch");
+    }
+    cudaError_t e = cudaMemcpyAsync(workspace, hbuf, hdr, cudaMemcpyHostToDevice, stream);
+    free(hbuf);
     LFD_CUDA_OK(e);
     const Plane *dd = (const Plane *)workspace;
     for (int phase = 0; phase < 3; ++phase) {
@@ -597,7 +696,8 @@ int launch_mft_czt(const lfd_mft_desc *descs, int count, void *workspace, size_t
             if (!(useA[lg] || useB[lg])) continue;
             int rc = 0;
             switch (lg) {
-#define LFD_CZT_CASE(LG) case LG: rc = launch_for_length<LG>(dd, count, max_m, max_N, useA[LG], useB[LG], phase, dev, nsm, stream); break;
+#define LFD_CZT_CASE(LG) case LG: rc = launch_for_length<LG>(dd, count, (const int *)(ws + starts_offset(count, 0, LG)), (int)unitsA[LG], \
+                                                             (const int *)(ws + starts_offset(count, 1, LG)), (int)unitsB[LG], phase, dev, nsm, stream); break;
                 LFD_CZT_CASE(6) LFD_CZT_CASE(7) LFD_CZT_CASE(8) LFD_CZT_CASE(9) LFD_CZT_CASE(10) LFD_CZT_CASE(11) LFD_CZT_CASE(12)
                 LFD_CZT_CASE(13)
 #undef LFD_CZT_CASE

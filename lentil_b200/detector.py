@@ -22,7 +22,11 @@ def rebin(img, factor):
     ValueError; host input keeps its dtype on the way out, device tensors come back as float64."""
     if np.iscomplexobj(img) if not device.is_dev(img) else img.is_complex():
         raise ValueError('rebin is not defined for complex data')
-    in_dtype = None if device.is_dev(img) else np.asarray(img).dtype
+    in_dtype = None
+    if not device.is_dev(img):
+        a = np.asarray(img)
+        # the reference sums numpy blocks: a cube keeps its dtype (util.py:250), a single image takes numpy's sum dtype
+        in_dtype = a.dtype if a.ndim == 3 else np.zeros(1, dtype=a.dtype).sum().dtype
     d, on_dev = _to_dev(img)
     planes = d.reshape((-1,) + tuple(d.shape[-2:]))
     h, w = int(planes.shape[1]), int(planes.shape[2])

@@ -35,7 +35,19 @@ def _workspace(nbytes):
     return ws
 
 
-def mft_descriptor(desc, f_dev, out_dev, alpha, shift, offset, unitary=True, inverse=False):
+EXECUTIONS = {None: 0, 'default': 0, 'direct': 1, 'folded': 2, 'czt': 3, 'auto': 4}    # lfd_mft_desc.execution
+
+
+def execution_code(execution):
+    """lfd_mft_desc.execution for a name: None = the process default (lfd_set_mft_variant / LFD_MFT_VARIANT), else the K2a
+    execution this call runs with ('direct' | 'folded' | 'czt' | 'auto'), independent of other threads and streams."""
+    try:
+        return EXECUTIONS[execution]
+    except KeyError:
+        raise ValueError(f"execution must be one of {sorted(k for k in EXECUTIONS if k)} or None, not {execution!r}")
+
+
+def mft_descriptor(desc, f_dev, out_dev, alpha, shift, offset, unitary=True, inverse=False, execution=None):
     """Fill one lfd_mft_desc for device arrays `f_dev` (m x n) -> `out_dev` (M x N)."""
     ar, ac = _pair(alpha)
     sr, sc = _pair(shift)
@@ -48,6 +60,7 @@ def mft_descriptor(desc, f_dev, out_dev, alpha, shift, offset, unitary=True, inv
     desc.shift_r, desc.shift_c = float(sr), float(sc)
     desc.off_r, desc.off_c = float(orow), float(ocol)
     desc.unitary, desc.inverse = int(bool(unitary)), int(bool(inverse))
+    desc.execution = execution_code(execution)
     return desc
 
 
@@ -116,7 +129,7 @@ def run_mft(descs, count, precision='c128', pupil_src=None, intensity_out=False)
 
 
 def dft2_dev(f_dev, alpha, shape=None, shift=(0, 0), offset=(0, 0), unitary=True, inverse=False,
-             out=None):
+             out=None, execution=None):
     """dft2 on device arrays; returns a complex128 device tensor (no host transfer)."""
     import torch
     m, n = int(f_dev.shape[0]), int(f_dev.shape[1])
@@ -125,38 +138,39 @@ def dft2_dev(f_dev, alpha, shape=None, shift=(0, 0), offset=(0, 0), unitary=True
     if out is None:
         out = torch.empty(M, N, dtype=f_dev.dtype, device=f_dev.device)
     descs = (_lib.MftDesc * 1)()
-    mft_descriptor(descs[0], f_dev, out, alpha, shift, offset, unitary, inverse)
+    mft_descriptor(descs[0], f_dev, out, alpha, shift, offset, unitary, inverse, execution)
     run_mft(descs, 1, 'c64' if c64 else 'c128')
     return out
 
 
-def _transform(f, alpha, shape, shift, offset, unitary, out, inverse):
+def _transform(f, alpha, shape, shift, offset, unitary, out, inverse, execution=None):
     if out is not None and not np.can_cast(complex, out.dtype):
         raise TypeError(f"Cannot cast complex output to dtype('{out.dtype}')")
     f = np.asarray(f)
     m, n = f.shape
     f_dev = device.to_dev(f, dtype=np.complex128)
-    F = device.to_host(dft2_dev(f_dev, alpha, shape, shift, offset, unitary, inverse))
+    F = device.to_host(dft2_dev(f_dev, alpha, shape, shift, offset, unitary, inverse, execution=execution))
     if out is not None:
         out[...] = F
         return out
     return F
 
 
-def dft2(f, alpha, shape=None, shift=(0, 0), offset=(0, 0), unitary=True, out=None):
+def dft2(f, alpha, shape=None, shift=(0, 0), offset=(0, 0), unitary=True, out=None, execution=None):
     """2-D discrete Fourier transform by matrix triple product (lentil/fourier.py:5-103).
 
     f : array_like (m, n); alpha : float or (row, col); shape : int or (M, N), default f.shape;
     shift : output-plane DC shift in pixels (r, c), may be fractional; offset : input-plane
     offset in pixels (r, c); unitary : scale by sqrt|alpha_r alpha_c|; out : optional result
-    array (must accept complex, else TypeError; may alias f)."""
-    return _transform(f, alpha, shape, shift, offset, unitary, out, inverse=False)
+    array (must accept complex, else TypeError; may alias f).  `execution` (not in the reference) picks the K2a execution
+    for this call: None = library default, 'direct' | 'folded' (FP64 tensor cores) | 'czt' | 'auto'."""
+    return _transform(f, alpha, shape, shift, offset, unitary, out, inverse=False, execution=execution)
 
 
-def idft2(F, alpha, shape=None, shift=(0, 0), unitary=True, out=None):
+def idft2(F, alpha, shape=None, shift=(0, 0), unitary=True, out=None, execution=None):
     """Inverse transform, conj(dft2(conj F)) / F.size (lentil/fourier.py:124-198): the
     conjugations fold into the twiddle sign, the division into the output scale."""
-    return _transform(F, alpha, shape, shift, (0, 0), unitary, out, inverse=True)
+    return _transform(F, alpha, shape, shift, (0, 0), unitary, out, inverse=True, execution=execution)
 
 
 def dft2_c64(f, alpha, shape=None, shift=(0, 0), offset=(0, 0), unitary=True):

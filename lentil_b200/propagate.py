@@ -218,7 +218,7 @@ def _shift_for(tilts, z, wavelength, du, oversample):
 
 def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, oversample=2,
                         mask=None, weights=None, tilts=None, opds=None, out=None, chunk_bytes=8 << 30,
-                        distributed=False, return_device=False, precision='c128'):
+                        distributed=False, return_device=False, precision='c128', execution=None):
     """Polychromatic, multi-field-point, multi-realisation PSF stack in one call.
 
     Equivalent to the reference user loop (docs/user/performance.rst:44-49)::
@@ -241,6 +241,8 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
     precision : 'c128' (default: lentil's arithmetic, FP64 tensor cores) or 'c64' (complex64 fields
         through the 3xTF32 tcgen05 path K2b; intensities are still accumulated in float64;
         peak-normalised PSF error ~1e-6 .. 1e-5)
+    execution : K2a execution of THIS call ('direct' | 'folded' = FP64 tensor cores | 'czt' | 'auto'); None = the library
+        default (LFD_MFT_AUTO unless lfd_set_mft_variant / LFD_MFT_VARIANT changed it)
 
     Returns ([R,] [P,] H, W): axes that were not requested are squeezed away.
 
@@ -329,7 +331,9 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
         # With one field point every phasor feeds exactly one transform: K1 is then fused into the fold
         # kernel of the folded K2a / of K2b (lfd_mft_c128_from_pupil, lfd_mft_c64x3_from_pupil) and phasors never exist in HBM; with a single
         # segment the column stage also squares the field itself (no coherent merge to do in K3).
-        fused = P == 1 and (c64 or _lib.lib().lfd_get_mft_variant() != 0)      # every execution but the direct one fuses K1
+        exec_code = _fourier.execution_code(execution)
+        direct = (exec_code == 1) if exec_code else (_lib.lib().lfd_get_mft_variant() == 0)
+        fused = P == 1 and (c64 or not direct)                              # every execution but the direct one fuses K1
         intensity_out = fused and nseg == 1
         if not fused:
             phasors = torch.empty(nw, ops['total'], dtype=cdtype, device=device.device())
@@ -396,6 +400,7 @@ def propagate_dft_batch(plane, wavelengths, pixelscale, shape, prop_shape=None, 
         D['shift_r'], D['shift_c'] = jdft[:, 0], jdft[:, 1]
         D['off_r'], D['off_c'] = offs[jn, 0], offs[jn, 1]
         D['unitary'] = 1
+        D['execution'] = exec_code
         for b0 in range(0, nj, _MAX_PLANES_PER_LAUNCH):                      # K2a
             nb = min(_MAX_PLANES_PER_LAUNCH, nj - b0)
             _fourier.run_mft(D[b0:b0 + nb].ctypes.data_as(C.POINTER(_lib.MftDesc)), nb, precision,

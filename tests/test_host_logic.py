@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match():
     L = _lib.lib()
-    assert L.lfd_abi_version() == 1
+    assert L.lfd_abi_version() == 2
     assert L.lfd_struct_size(0) == ctypes.sizeof(_lib.MftDesc)
     assert L.lfd_struct_size(1) == ctypes.sizeof(_lib.Segment)
     assert L.lfd_struct_size(2) == ctypes.sizeof(_lib.Window)
