@@ -114,7 +114,15 @@ int lfd_mft_c128_from_pupil(const lfd_mft_desc *descs_host, const lfd_pupil_src 
  * Same descriptor, but `f` and `out` are complex64 (interleaved floats).  Every real product is
  * evaluated as hi*hi + hi*lo + lo*hi in TF32 with fp32 accumulation in TMEM; peak-normalised error
  * ~1e-6 (gate 1e-5).  lentil itself has no complex64 mode (Field casts to complex128,
- * lentil/field.py:35): this is the optional fast path BASELINE.json's north star names. */
+ * lentil/field.py:35): this is the optional fast path BASELINE.json's north star names.
+ *
+ * Two executions, chosen like K2a's (lfd_mft_desc.execution of the first plane, else the process default):
+ *   LFD_MFT_DIRECT / LFD_MFT_FOLDED : the folded transform as 3xTF32 tcgen05 MMAs (mft_c64.cu)
+ *   LFD_MFT_CZT / LFD_MFT_AUTO      : the FP32 build of the chirp-z row transform (mft_czt.cu; chirps and the transformed
+ *                                     chirp filter are built in float64 and rounded once) whenever every plane fits it,
+ *                                     else the tcgen05 form.  Peak-normalised error ~3e-7 at any size.
+ * lfd_mft_c64_execution reports which one a batch runs (LFD_MFT_FOLDED = tcgen05, LFD_MFT_CZT = chirp-z). */
+int    lfd_mft_c64_execution(const lfd_mft_desc *descs_host, int count);
 size_t lfd_mft_c64x3_workspace_bytes(const lfd_mft_desc *descs_host, int count);
 int lfd_mft_c64x3_batched(const lfd_mft_desc *descs_host, int count,
                           void *workspace_dev, size_t workspace_bytes, void *stream);

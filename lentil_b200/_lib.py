@@ -72,6 +72,7 @@ SIGNATURES = {
     "lfd_mft_c128": (C.c_int, [C.POINTER(MftDesc), C.c_void_p, C.c_size_t, C.c_void_p]),
     "lfd_mft_c128_from_pupil": (C.c_int, [C.POINTER(MftDesc), C.POINTER(PupilSrc), C.c_int, C.c_int, C.c_void_p,
                                           C.c_size_t, C.c_void_p]),
+    "lfd_mft_c64_execution": (C.c_int, [C.POINTER(MftDesc), C.c_int]),
     "lfd_mft_c64x3_workspace_bytes": (C.c_size_t, [C.POINTER(MftDesc), C.c_int]),
     "lfd_mft_c64x3_batched": (C.c_int, [C.POINTER(MftDesc), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "lfd_mft_c64x3_from_pupil": (C.c_int, [C.POINTER(MftDesc), C.POINTER(PupilSrc), C.c_int, C.c_int, C.c_void_p,

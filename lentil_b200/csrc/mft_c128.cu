@@ -188,9 +188,9 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
 
 bool czt_supported(const lfd_mft_desc *descs, int count);
 bool czt_preferred(const lfd_mft_desc *descs, int count);
-size_t czt_workspace_bytes(const lfd_mft_desc *descs, int count);
+size_t czt_workspace_bytes(const lfd_mft_desc *descs, int count, bool c64);
 int launch_mft_czt(const lfd_mft_desc *descs, int count, void *workspace, size_t workspace_bytes, cudaStream_t stream,
-                   const lfd_pupil_src *src, int intensity_out);
+                   const lfd_pupil_src *src, int intensity_out, bool c64);
 
 static std::atomic<int> g_variant{LFD_MFT_AUTO};
 
@@ -220,7 +220,7 @@ extern "C" int lfd_mft_execution(const lfd_mft_desc *descs, int count) {
 
 extern "C" size_t lfd_mft_workspace_bytes(const lfd_mft_desc *descs, int count) {
     const int variant = mft_resolve_execution(descs, count);
-    if (variant == LFD_MFT_CZT) return czt_workspace_bytes(descs, count);
+    if (variant == LFD_MFT_CZT) return czt_workspace_bytes(descs, count, false);
     if (variant == LFD_MFT_FOLDED) return folded_workspace_bytes(descs, count);
     size_t bytes = align_up((size_t)2 * count * sizeof(StageDesc), 256);
     for (int i = 0; i < count; ++i)
@@ -236,7 +236,7 @@ extern "C" int lfd_mft_c128_batched(const lfd_mft_desc *descs, int count, void *
     LFD_REQUIRE(workspace != nullptr, "lfd_mft_c128_batched: workspace is NULL");
     const int variant = mft_resolve_execution(descs, count);
     if (variant == LFD_MFT_CZT)
-        return launch_mft_czt(descs, count, workspace, workspace_bytes, stream, nullptr, 0);
+        return launch_mft_czt(descs, count, workspace, workspace_bytes, stream, nullptr, 0, false);
     if (variant != LFD_MFT_DIRECT)
         return launch_mft_folded(descs, count, workspace, workspace_bytes, stream, nullptr, 0);
     size_t need = lfd_mft_workspace_bytes(descs, count);

@@ -862,18 +862,41 @@ int launch_mft_c64(const lfd_mft_desc *descs, int count, void *workspace, size_t
 }  // namespace c64
 }  // namespace lfd
 
+// Two executions of the complex64 mode: the folded 3xTF32 form on tcgen05 (this file) and the FP32 build of the chirp-z
+// row transform (mft_czt.cu).  lfd_mft_desc.execution of the first plane, else the process default, decides:
+// DIRECT / FOLDED -> tcgen05, CZT / AUTO -> chirp-z whenever every plane fits it (FFT length <= 8192).
+namespace lfd {
+int mft_resolve_execution(const lfd_mft_desc *descs, int count);
+bool czt_supported(const lfd_mft_desc *descs, int count);
+size_t czt_workspace_bytes(const lfd_mft_desc *descs, int count, bool c64);
+int launch_mft_czt(const lfd_mft_desc *descs, int count, void *workspace, size_t workspace_bytes, cudaStream_t stream,
+                   const lfd_pupil_src *src, int intensity_out, bool c64);
+static bool c64_runs_czt(const lfd_mft_desc *descs, int count) {
+    return descs && count > 0 && mft_resolve_execution(descs, count) == LFD_MFT_CZT && czt_supported(descs, count);
+}
+}  // namespace lfd
+
+extern "C" int lfd_mft_c64_execution(const lfd_mft_desc *descs, int count) {
+    return lfd::c64_runs_czt(descs, count) ? LFD_MFT_CZT : LFD_MFT_FOLDED;
+}
+
 extern "C" size_t lfd_mft_c64x3_workspace_bytes(const lfd_mft_desc *descs, int count) {
+    if (lfd::c64_runs_czt(descs, count)) return lfd::czt_workspace_bytes(descs, count, true);
     return lfd::c64::c64_workspace_bytes(descs, count);
 }
 
 extern "C" int lfd_mft_c64x3_batched(const lfd_mft_desc *descs, int count, void *workspace,
                                      size_t workspace_bytes, void *stream) {
+    if (lfd::c64_runs_czt(descs, count))
+        return lfd::launch_mft_czt(descs, count, workspace, workspace_bytes, (cudaStream_t)stream, nullptr, 0, true);
     return lfd::c64::launch_mft_c64(descs, count, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int lfd_mft_c64x3_from_pupil(const lfd_mft_desc *descs, const lfd_pupil_src *src, int count, int intensity_out,
                                         void *workspace, size_t workspace_bytes, void *stream) {
     LFD_REQUIRE(descs && src && workspace && count > 0, "lfd_mft_c64x3_from_pupil: bad arguments");
+    if (lfd::c64_runs_czt(descs, count))
+        return lfd::launch_mft_czt(descs, count, workspace, workspace_bytes, (cudaStream_t)stream, src, intensity_out, true);
     return lfd::c64::launch_mft_c64(descs, count, workspace, workspace_bytes, (cudaStream_t)stream, src, intensity_out);
 }
 

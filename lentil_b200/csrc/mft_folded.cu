@@ -42,7 +42,7 @@
 namespace lfd {
 int mft_resolve_execution(const lfd_mft_desc *descs, int count);
 int launch_mft_czt(const lfd_mft_desc *descs, int count, void *workspace, size_t workspace_bytes, cudaStream_t stream,
-                   const lfd_pupil_src *src, int intensity_out);
+                   const lfd_pupil_src *src, int intensity_out, bool c64);
 }
 namespace lfd {
 
@@ -654,6 +654,6 @@ extern "C" int lfd_mft_c128_from_pupil(const lfd_mft_desc *descs, const lfd_pupi
     if (count == 0) return 0;
     LFD_REQUIRE(descs && src && workspace && count > 0, "lfd_mft_c128_from_pupil: bad arguments");
     if (lfd::mft_resolve_execution(descs, count) == LFD_MFT_CZT)
-        return lfd::launch_mft_czt(descs, count, workspace, workspace_bytes, (cudaStream_t)stream, src, intensity_out);
+        return lfd::launch_mft_czt(descs, count, workspace, workspace_bytes, (cudaStream_t)stream, src, intensity_out, false);
     return lfd::launch_mft_folded(descs, count, workspace, workspace_bytes, (cudaStream_t)stream, src, intensity_out);
 }

@@ -22,11 +22,11 @@ _workspaces = {}
 
 
 def _workspace(nbytes):
-    """Grow-only scratch buffer per CUDA stream: launches on one stream are ordered, so the planes of the next
+    """Grow-only scratch buffer per (device, CUDA stream): launches on one stream are ordered, so the planes of the next
     call may reuse the intermediates of the previous one (saves an allocation per call of the drop-in loop)."""
     if nbytes > (256 << 20):            # big batches: leave it to torch's caching allocator
         return device.empty_bytes(nbytes)
-    key = device.stream_ptr()
+    key = (device.device().index, device.stream_ptr())      # the default stream is 0 on every device: key by device too
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         if len(_workspaces) > 8:
@@ -173,14 +173,15 @@ def idft2(F, alpha, shape=None, shift=(0, 0), unitary=True, out=None, execution=
     return _transform(F, alpha, shape, shift, (0, 0), unitary, out, inverse=True, execution=execution)
 
 
-def dft2_c64(f, alpha, shape=None, shift=(0, 0), offset=(0, 0), unitary=True):
-    """dft2 with complex64 input/output on the 3xTF32 tensor-core path (K2b).  Not part of the
-    reference surface (lentil is complex128 throughout): the optional fast mode of the north star,
-    peak-normalised error ~1e-6."""
+def dft2_c64(f, alpha, shape=None, shift=(0, 0), offset=(0, 0), unitary=True, execution=None):
+    """dft2 with complex64 input/output (K2b).  Not part of the reference surface (lentil is complex128
+    throughout): the optional fast mode of the north star.  execution 'folded' = the 3xTF32 tensor-core
+    (tcgen05) form, peak-normalised error ~1e-6 (growing with the input size); 'czt' / 'auto' / None =
+    the FP32 chirp-z form wherever the planes fit it, ~3e-7 at any size."""
     f_dev = device.to_dev(np.asarray(f), dtype=np.complex64)
-    return device.to_host(dft2_dev(f_dev, alpha, shape, shift, offset, unitary, inverse=False))
+    return device.to_host(dft2_dev(f_dev, alpha, shape, shift, offset, unitary, inverse=False, execution=execution))
 
 
-def idft2_c64(F, alpha, shape=None, shift=(0, 0), unitary=True):
+def idft2_c64(F, alpha, shape=None, shift=(0, 0), unitary=True, execution=None):
     f_dev = device.to_dev(np.asarray(F), dtype=np.complex64)
-    return device.to_host(dft2_dev(f_dev, alpha, shape, shift, (0, 0), unitary, inverse=True))
+    return device.to_host(dft2_dev(f_dev, alpha, shape, shift, (0, 0), unitary, inverse=True, execution=execution))

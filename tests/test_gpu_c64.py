@@ -10,6 +10,20 @@ from conftest import peak_err
 pytestmark = pytest.mark.gpu
 TOL32 = 1e-5
 
+
+@pytest.fixture(params=["tcgen05", "czt"], autouse=True)
+def c64_execution(request):
+    """Every test of this file runs under both executions of the complex64 mode: the folded 3xTF32 transform on tcgen05
+    (process default LFD_MFT_FOLDED) and the FP32 chirp-z row transform (LFD_MFT_AUTO, the default)."""
+    from lentil_b200 import _lib
+    L = _lib.lib()
+    L.lfd_set_mft_variant(1 if request.param == "tcgen05" else 3)
+    d = (_lib.MftDesc * 1)()
+    d[0].m = d[0].n = d[0].M = d[0].N = 64
+    assert L.lfd_mft_c64_execution(d, 1) == (1 if request.param == "tcgen05" else 2)
+    yield request.param
+    L.lfd_set_mft_variant(3)
+
 CASES = [
     (10, 10, 10, 10, 0.1, (0, 0), (0, 0), True),
     (11, 13, 17, 9, (1 / 11, 1 / 13), (0.3, -1.7), (2, -3), True),

@@ -47,11 +47,14 @@ def test_cfg5_plane_auto_is_chirpz():
     assert _lib.lib().lfd_mft_execution(d, 1) == 2                    # 6128 -> 8192 points: inside the chirp-z kernel
 
 
-@pytest.mark.xfail(reason="K2b's truncating fp32 accumulation (mft_c64.cu: 6.2e-9 x K of a coherent sum) reaches 1.7e-5 of the "
-                          "peak on a DENSE RANDOM field at K = 4081; physical apertures (next test) stay at 6e-6", strict=False)
-def test_cfg5_plane_c64(cfg5_plane):
+@pytest.mark.parametrize("execution", [
+    "czt",
+    pytest.param("folded", marks=pytest.mark.xfail(
+        reason="the tcgen05 form's truncating fp32 accumulation (mft_c64.cu: 6.2e-9 x K of a coherent sum) reaches 1.7e-5 of the "
+               "peak on a DENSE RANDOM field at K = 4081; physical apertures (next test) stay at 6e-6", strict=False))])
+def test_cfg5_plane_c64(cfg5_plane, execution):
     f, alpha, kw, ref = cfg5_plane
-    got = lentil.fourier.dft2_c64(f.astype(np.complex64), alpha, **kw)
+    got = lentil.fourier.dft2_c64(f.astype(np.complex64), alpha, execution=execution, **kw)
     assert got.dtype == np.complex64
     assert peak_err(got, ref) <= TOL32
 
@@ -66,8 +69,10 @@ def test_cfg5_coherent_psf_c64_and_fp64():
     p = lentil.Pupil(amplitude=amp, opd=opd, pixelscale=dx, focal_length=z)
     got = lentil.propagate_dft_batch(p, [650e-9], du, (1024, 1024), oversample=2, tilts=[[5e-6, -3e-6]])
     assert peak_err(got[0], ref) <= TOL64
-    got32 = lentil.propagate_dft_batch(p, [650e-9], du, (1024, 1024), oversample=2, tilts=[[5e-6, -3e-6]], precision='c64')
-    assert peak_err(got32[0], ref) <= TOL32
+    for execution in ("czt", "folded"):                 # FP32 chirp-z, and 3xTF32 on tcgen05
+        got32 = lentil.propagate_dft_batch(p, [650e-9], du, (1024, 1024), oversample=2, tilts=[[5e-6, -3e-6]], precision='c64',
+                                           execution=execution)
+        assert peak_err(got32[0], ref) <= TOL32, execution
 
 
 def test_cfg3_full_18_hex_fit_tilt():
@@ -91,8 +96,9 @@ def test_cfg3_full_18_hex_fit_tilt():
     for execution in ("auto", "folded"):
         got = lentil.propagate_dft_batch(p, wls, du, (256, 256), oversample=2, weights=wts, execution=execution)
         assert peak_err(got, ref) <= TOL64, execution
-    got32 = lentil.propagate_dft_batch(p, wls, du, (256, 256), oversample=2, weights=wts, precision='c64')
-    assert peak_err(got32, ref) <= TOL32
+    for execution in ("czt", "folded"):
+        got32 = lentil.propagate_dft_batch(p, wls, du, (256, 256), oversample=2, weights=wts, precision='c64', execution=execution)
+        assert peak_err(got32, ref) <= TOL32, execution
     # the drop-in loop (one Wavefront * Pupil -> propagate_dft -> insert per wavelength) gives the same image
     loop = np.zeros((512, 512))
     for wl, wt in zip(wls, wts):
