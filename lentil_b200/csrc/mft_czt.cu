@@ -30,7 +30,9 @@
 //  * L <= 8192: one buffer of L complex128 (139 KB with padding) is the most that fits the 227 KB of an SM; longer
 //    transforms use the folded DMMA execution (the dispatcher in mft_c128.cu decides).
 #include "lfd_common.cuh"
+#include <map>
 #include <mutex>
+#include <tuple>
 
 namespace lfd {
 namespace czt {
@@ -348,6 +350,12 @@ int launch_mft_czt(const lfd_mft_desc *descs, int count, void *workspace, size_t
     size_t off = hdr;
     bool useA[MAX_LOG2L + 1] = {false}, useB[MAX_LOG2L + 1] = {false};
     long long unitsA[MAX_LOG2L + 1] = {0}, unitsB[MAX_LOG2L + 1] = {0};
+    // Planes whose row stage is the SAME computation — same input (array or pupil window and wavelength) and the same column
+    // geometry (n -> N, alpha_c, offset, shift) — share one stage-A result: field points that differ only in their row shift
+    // (a grid of field points, BASELINE configs[4]) transform their rows once.  Same arithmetic, so results are unchanged.
+    typedef std::tuple<const void *, long long, const void *, const void *, const void *, int, int, int, double,
+                       int, int, int, double, double, double, int> StageAKey;
+    std::map<StageAKey, int> leaders;
     for (int i = 0; i < count; ++i) {
         const lfd_mft_desc &p = descs[i];
         const bool ok = p.m > 0 && p.n > 0 && p.M > 0 && p.N > 0 && p.ldo >= p.N && p.out &&
@@ -380,13 +388,19 @@ int launch_mft_czt(const lfd_mft_desc *descs, int count, void *workspace, size_t
             d.inv_wavelength = 1.0 / src[i].wavelength;
         }
         useA[d.logLA] = true; useB[d.logLB] = true;
+        const StageAKey key(src ? nullptr : p.f, src ? 0 : p.ldf, d.amp, d.opd, d.mask, src ? src[i].n_c : 0, d.pr0, d.pc0,
+                            src ? d.wavelength : 0.0, p.m, p.n, p.N, p.alpha_c, p.off_c, p.shift_c, p.inverse ? 1 : 0);
+        const auto lead = leaders.find(key);
+        const bool shared = lead != leaders.end();
+        if (shared) d.Gt = h[lead->second].Gt;          // stage B reads the leader's transposed intermediate
+        else leaders.emplace(key, i);
         // unit start tables: stage A deals the m input rows of the plane, stage B the N columns, ROWS at a time
         for (int lg = MIN_LOG2L; lg <= MAX_LOG2L; ++lg) {
             int *sa = (int *)(hbuf + starts_offset(count, 0, lg)), *sb = (int *)(hbuf + starts_offset(count, 1, lg));
             sa[i] = (int)unitsA[lg]; sb[i] = (int)unitsB[lg];
         }
         const int ra = rows_for_length(d.logLA), rb = rows_for_length(d.logLB);
-        unitsA[d.logLA] += (p.m + ra - 1) / ra;
+        unitsA[d.logLA] += shared ? 0 : (p.m + ra - 1) / ra;
         unitsB[d.logLB] += (p.N + rb - 1) / rb;
     }
     bool too_many = false;
