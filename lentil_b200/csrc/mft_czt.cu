@@ -33,6 +33,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <type_traits>
 
 namespace lfd {
 namespace czt {

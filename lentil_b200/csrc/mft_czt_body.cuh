@@ -36,10 +36,19 @@ template <int S> __device__ __forceinline__ void dft8(V2 (&v)[8]) {
 }
 // 16-point DFT, natural order in and out, as 4 x 4: n = 4 n1 + n2, k = k1 + 4 k2,
 //   X[k1 + 4 k2] = sum_n2 w4^(n2 k2) [ w16^(n2 k1) sum_n1 x[4 n1 + n2] w4^(n1 k1) ]
-template <int S> __device__ __forceinline__ void dft16(V2 (&v)[16]) {
+// IN8: the inputs v[8..15] are zero (a zero-padded row: n_in <= L / 2) and are not read; OUT8: only the outputs v[0..7] are
+// wanted (n_out <= L / 2), v[8..15] are left undefined.  Both save the additions that would handle zeros / unused sums.
+template <int S, bool IN8 = false, bool OUT8 = false> __device__ __forceinline__ void dft16(V2 (&v)[16]) {
     const RL h = (RL)0.70710678118654752440, c1 = (RL)0.92387953251128675613, s1 = (RL)0.38268343236508977173;
 #pragma unroll
-    for (int n2 = 0; n2 < 4; ++n2) dft4<S>(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);      // -> y[n2][k1] at v[4 k1 + n2]
+    for (int n2 = 0; n2 < 4; ++n2) {                                                        // -> y[n2][k1] at v[4 k1 + n2]
+        if constexpr (IN8) {
+            const V2 x0 = v[n2], x1 = v[4 + n2], m = mul_mi<S>(x1);
+            v[n2] = cadd(x0, x1); v[4 + n2] = cadd(x0, m); v[8 + n2] = csub(x0, x1); v[12 + n2] = csub(x0, m);
+        } else {
+            dft4<S>(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+        }
+    }
     v[5]  = mul_root<S>(v[5], c1, s1);        // k1 = 1: w16^1, w16^2, w16^3
     v[6]  = mul_root<S>(v[6], h, h);
     v[7]  = mul_root<S>(v[7], s1, c1);
@@ -49,13 +58,25 @@ template <int S> __device__ __forceinline__ void dft16(V2 (&v)[16]) {
     v[13] = mul_root<S>(v[13], s1, c1);       // k1 = 3: w16^3, w16^6, w16^9
     v[14] = mul_root<S>(v[14], -h, h);
     v[15] = mul_root<S>(v[15], -c1, -s1);
+    if constexpr (OUT8) {                     // X[k1] (k2 = 0) and X[k1 + 4] (k2 = 1) only
+        V2 lo[4], hi[4];
 #pragma unroll
-    for (int k1 = 0; k1 < 4; ++k1) dft4<S>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);   // X[k1 + 4 k2] at v[4 k1 + k2]
-    // 4 x 4 transpose of the register names
+        for (int k1 = 0; k1 < 4; ++k1) {
+            const V2 a0 = v[4 * k1], a1 = v[4 * k1 + 1], a2 = v[4 * k1 + 2], a3 = v[4 * k1 + 3];
+            lo[k1] = cadd(cadd(a0, a2), cadd(a1, a3));
+            hi[k1] = cadd(csub(a0, a2), mul_mi<S>(csub(a1, a3)));
+        }
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+        for (int k1 = 0; k1 < 4; ++k1) { v[k1] = lo[k1]; v[4 + k1] = hi[k1]; }
+    } else {
 #pragma unroll
-        for (int b = a + 1; b < 4; ++b) { const V2 x = v[4 * a + b]; v[4 * a + b] = v[4 * b + a]; v[4 * b + a] = x; }
+        for (int k1 = 0; k1 < 4; ++k1) dft4<S>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);   // X[k1 + 4 k2] at v[4 k1 + k2]
+        // 4 x 4 transpose of the register names
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = a + 1; b < 4; ++b) { const V2 x = v[4 * a + b]; v[4 * a + b] = v[4 * b + a]; v[4 * b + a] = x; }
+    }
 }
 template <int R, int S> __device__ __forceinline__ void dftR(V2 (&v)[R]) {
     if constexpr (R == 16) dft16<S>(v);
@@ -113,14 +134,17 @@ __device__ __forceinline__ void turn(V2 *X, const V2 *hv, int t, int q, V2 w1) {
 // global memory — its twiddle, the 16 values of H for the turn, the first eight post-chirp factors for the last pass — is
 // fetched BEFORE the barrier that precedes the pass: the data registers are dead there (the row lives in shared memory),
 // and the load latency overlaps the barrier wait instead of the arithmetic.
-template <int LOG2L, int ROWS, int NBUF, class Load16, class Store16>
+// HALF: n_in <= L / 2 and n_out <= L / 2 (the usual case: L is the power of two above n_in + n_out): the loader fills only
+// v[0..7], the first butterfly skips the zero half, the last one computes only the wanted half, the store writes v[0..7].
+template <int LOG2L, int ROWS, int NBUF, bool HALF, class Load16, class Store16>
 __device__ __forceinline__ void czt_row(V2 *&X, V2 *&Y, int t, const Load16 &load16, const V2 *__restrict__ H,
                                         const V2 *__restrict__ post, int nout, const Store16 &store16) {
     constexpr int L = 1 << LOG2L, T = L / 16, NREG = nreg(LOG2L), RT = turn_radix(LOG2L), NB = 16 / RT, NS = L / RT;
     const V2 *__restrict__ tw = tw_table(LOG2L);
+    const std::integral_constant<bool, HALF> half_tag;
     V2 v[16];
-    load16(v);
-    dft16<1>(v);
+    load16(v, half_tag);
+    dft16<1, HALF, false>(v);
 #pragma unroll
     for (int r = 0; r < 16; ++r) X[(17 * t + r) * ROWS] = v[r];          // = slot(16 t + r)
     int Ns = 16;
@@ -178,16 +202,16 @@ __device__ __forceinline__ void czt_row(V2 *&X, V2 *&Y, int t, const Load16 &loa
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = X[(17 * t + r) * ROWS];
-    dft16<-1>(v);
+    dft16<-1, false, HALF>(v);
 #pragma unroll
     for (int sI = 0; sI < PP; ++sI) v[sI] = cmul(v[sI], pv[sI]);
 #pragma unroll
     for (int sI = PP; sI < 8; ++sI) v[sI] = (t + sI * T < nout) ? cmul(v[sI], post[t + sI * T]) : v[sI];
-    if (8 * T < nout) {                                    // uniform; outputs beyond half the transform length are rare
+    if (!HALF && 8 * T < nout) {                           // uniform; outputs beyond half the transform length are rare
 #pragma unroll
         for (int sI = 8; sI < 16; ++sI) v[sI] = (t + sI * T < nout) ? cmul(v[sI], post[t + sI * T]) : v[sI];
     }
-    store16(v);
+    store16(v, half_tag);
     if (NBUF == 1) __syncthreads();
     else { V2 *x = X; X = Y; Y = x; }
 }
@@ -266,28 +290,46 @@ czt_stage_kernel(const Plane *__restrict__ descs, const int *__restrict__ starts
             }
         }
         // first forward pass: the inputs of this thread straight from global memory (x pre-chirp; zero beyond the input
-        // length), in two halves of eight so that every load of a half is issued before its arithmetic
-        auto load = [=](V2 (&v)[16]) {
+        // length), in halves of eight so that every load of a half is issued before its arithmetic.  Threads whose eight
+        // elements are all inside the row (every thread but those at the row's end) take the unpredicated path.
+        auto load = [=](V2 (&v)[16], auto half_tag) {
+            constexpr bool HALF = decltype(half_tag)::value;
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                if (hf * 8 * T >= nin) {                                 // uniform: this half lies beyond the input
+            for (int hf = 0; hf < (HALF ? 1 : 2); ++hf) {
+                if (!HALF && hf * 8 * T >= nin) {                        // uniform: this half lies beyond the input
 #pragma unroll
                     for (int s = 0; s < 8; ++s) v[hf * 8 + s] = mk2((RL)0, (RL)0);
                     continue;
                 }
+                const bool all_in = rv && t + (hf * 8 + 7) * T < nin;
                 V2 pr[8];
                 if (STAGE_A && dp->amp != nullptr) {
                     double am[8], op[8];
                     const long long base = (long long)(dp->pr0 + row) * dp->pld + dp->pc0;
                     const unsigned char *mk = dp->mask;
+                    if (all_in) {
 #pragma unroll
-                    for (int s = 0; s < 8; ++s) {
-                        const int i = t + (hf * 8 + s) * T;
-                        const bool in = rv && i < nin;
-                        am[s] = in ? dp->amp[base + i] : 0.0;
-                        op[s] = in ? dp->opd[base + i] : 0.0;
-                        pr[s] = in ? pre[i] : mk2((RL)0, (RL)0);
-                        if (in && mk != nullptr && mk[base + i] == 0) am[s] = 0.0;
+                        for (int s = 0; s < 8; ++s) {
+                            const int i = t + (hf * 8 + s) * T;
+                            am[s] = dp->amp[base + i];
+                            op[s] = dp->opd[base + i];
+                            pr[s] = pre[i];
+                        }
+                        if (mk != nullptr) {
+#pragma unroll
+                            for (int s = 0; s < 8; ++s)
+                                if (mk[base + t + (hf * 8 + s) * T] == 0) am[s] = 0.0;
+                        }
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < 8; ++s) {
+                            const int i = t + (hf * 8 + s) * T;
+                            const bool in = rv && i < nin;
+                            am[s] = in ? dp->amp[base + i] : 0.0;
+                            op[s] = in ? dp->opd[base + i] : 0.0;
+                            pr[s] = in ? pre[i] : mk2((RL)0, (RL)0);
+                            if (in && mk != nullptr && mk[base + i] == 0) am[s] = 0.0;
+                        }
                     }
                     const double lam = dp->wavelength, inv_lam = dp->inv_wavelength;
 #pragma unroll
@@ -299,48 +341,81 @@ czt_stage_kernel(const Plane *__restrict__ descs, const int *__restrict__ starts
                 } else {
                     const V2 *src = STAGE_A ? (const V2 *)dp->f + (long long)row * dp->ldf : (const V2 *)dp->Gt + (long long)row * dp->mpad;
                     V2 x[8];
+                    if (all_in) {
 #pragma unroll
-                    for (int s = 0; s < 8; ++s) {
-                        const int i = t + (hf * 8 + s) * T;
-                        const bool in = rv && i < nin;
-                        x[s] = in ? src[i] : mk2((RL)0, (RL)0);
-                        pr[s] = in ? pre[i] : mk2((RL)0, (RL)0);
+                        for (int s = 0; s < 8; ++s) {
+                            const int i = t + (hf * 8 + s) * T;
+                            x[s] = src[i];
+                            pr[s] = pre[i];
+                        }
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < 8; ++s) {
+                            const int i = t + (hf * 8 + s) * T;
+                            const bool in = rv && i < nin;
+                            x[s] = in ? src[i] : mk2((RL)0, (RL)0);
+                            pr[s] = in ? pre[i] : mk2((RL)0, (RL)0);
+                        }
                     }
 #pragma unroll
                     for (int s = 0; s < 8; ++s) v[hf * 8 + s] = cmul(x[s], pr[s]);
                 }
             }
         };
+        // the usual case: both the input and the wanted output fit half the transform length (uniform over the plane)
+        const bool half = nin <= 8 * T && nout <= 8 * T;
+        const bool all_out = rv && t + 7 * T < nout;
         if (STAGE_A) {
-            V2 *Gt = (V2 *)dp->Gt; const long long mpad = dp->mpad;
-            auto store = [=](V2 (&v)[16]) {
+            V2 *Gt = (V2 *)dp->Gt + row; const long long mpad = dp->mpad;
+            auto store = [=](V2 (&v)[16], auto half_tag) {
+                constexpr int NS_ = decltype(half_tag)::value ? 8 : 16;
+                if (decltype(half_tag)::value && all_out) {
 #pragma unroll
-                for (int s = 0; s < 16; ++s) {
+                    for (int s = 0; s < 8; ++s) Gt[(long long)(t + s * T) * mpad] = v[s];
+                    return;
+                }
+#pragma unroll
+                for (int s = 0; s < NS_; ++s) {
                     const int i = t + s * T;
-                    if (rv && i < nout) Gt[(long long)i * mpad + row] = v[s];
+                    if (rv && i < nout) Gt[(long long)i * mpad] = v[s];
                 }
             };
-            czt_row<LOG2L, ROWS, NBUF>(X, Y, t, load, H, post, nout, store);
+            if (half) czt_row<LOG2L, ROWS, NBUF, true>(X, Y, t, load, H, post, nout, store);
+            else czt_row<LOG2L, ROWS, NBUF, false>(X, Y, t, load, H, post, nout, store);
         } else if (dp->intensity) {
-            double *out = (double *)dp->out; const long long ldo = dp->ldo;
-            auto store = [=](V2 (&v)[16]) {
+            double *out = (double *)dp->out + row; const long long ldo = dp->ldo;
+            auto store = [=](V2 (&v)[16], auto half_tag) {
+                constexpr int NS_ = decltype(half_tag)::value ? 8 : 16;
+                if (decltype(half_tag)::value && all_out) {
 #pragma unroll
-                for (int s = 0; s < 16; ++s) {
+                    for (int s = 0; s < 8; ++s) out[(long long)(t + s * T) * ldo] = (double)v[s].x * (double)v[s].x + (double)v[s].y * (double)v[s].y;
+                    return;
+                }
+#pragma unroll
+                for (int s = 0; s < NS_; ++s) {
                     const int i = t + s * T;
-                    if (rv && i < nout) out[(long long)i * ldo + row] = (double)v[s].x * (double)v[s].x + (double)v[s].y * (double)v[s].y;
+                    if (rv && i < nout) out[(long long)i * ldo] = (double)v[s].x * (double)v[s].x + (double)v[s].y * (double)v[s].y;
                 }
             };
-            czt_row<LOG2L, ROWS, NBUF>(X, Y, t, load, H, post, nout, store);
+            if (half) czt_row<LOG2L, ROWS, NBUF, true>(X, Y, t, load, H, post, nout, store);
+            else czt_row<LOG2L, ROWS, NBUF, false>(X, Y, t, load, H, post, nout, store);
         } else {
-            V2 *out = (V2 *)dp->out; const long long ldo = dp->ldo;
-            auto store = [=](V2 (&v)[16]) {
+            V2 *out = (V2 *)dp->out + row; const long long ldo = dp->ldo;
+            auto store = [=](V2 (&v)[16], auto half_tag) {
+                constexpr int NS_ = decltype(half_tag)::value ? 8 : 16;
+                if (decltype(half_tag)::value && all_out) {
 #pragma unroll
-                for (int s = 0; s < 16; ++s) {
+                    for (int s = 0; s < 8; ++s) out[(long long)(t + s * T) * ldo] = v[s];
+                    return;
+                }
+#pragma unroll
+                for (int s = 0; s < NS_; ++s) {
                     const int i = t + s * T;
-                    if (rv && i < nout) out[(long long)i * ldo + row] = v[s];
+                    if (rv && i < nout) out[(long long)i * ldo] = v[s];
                 }
             };
-            czt_row<LOG2L, ROWS, NBUF>(X, Y, t, load, H, post, nout, store);
+            if (half) czt_row<LOG2L, ROWS, NBUF, true>(X, Y, t, load, H, post, nout, store);
+            else czt_row<LOG2L, ROWS, NBUF, false>(X, Y, t, load, H, post, nout, store);
         }
     }
 }
