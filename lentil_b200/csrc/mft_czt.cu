@@ -71,6 +71,9 @@ __device__ float2 g_twf[MAX_LOG2L - MIN_LOG2L + 1][TW_PER_LEN];      // the same
 #ifndef LFD_CZT_CONTIG
 #define LFD_CZT_CONTIG 0      // 1: one contiguous run of work units per CTA instead of the round-robin deal (see czt_stage_kernel)
 #endif
+#ifndef LFD_CZT_F64_THREADS
+#define LFD_CZT_F64_THREADS 512
+#endif
 #ifndef LFD_CZT_F32_THREADS
 #define LFD_CZT_F32_THREADS 768
 #endif
@@ -121,12 +124,13 @@ struct Plane {
 namespace f64 {
 using RL = double;
 using V2 = double2;
-constexpr int REG_THREADS = 512;                  // 128 registers per thread
+constexpr int REG_THREADS = LFD_CZT_F64_THREADS;  // threads per SM the register allocation must allow (512 -> 128 registers)
 __device__ __forceinline__ V2 mk2(RL x, RL y) { return make_double2(x, y); }
 __device__ __forceinline__ const V2 *tw_table(int lg) { return g_tw[lg - MIN_LOG2L]; }
-// amp * exp(2 pi i opd / lambda): phase in cycles, reduced exactly (the arithmetic of K1, pupil_prep.cu)
-__device__ __forceinline__ V2 phasor(double am, double op, double lam, double) {
-    const double tcyc = op / lam;
+// amp * exp(2 pi i opd / lambda): phase in cycles, reduced exactly (K1's arithmetic, pupil_prep.cu, with the division by
+// lambda replaced by a multiplication with its rounded reciprocal: at most one ulp of the phase in cycles, ~1e-16 rad)
+__device__ __forceinline__ V2 phasor(double am, double op, double, double inv_lam) {
+    const double tcyc = op * inv_lam;
     double sn, cs;
     sincospi(2.0 * (tcyc - rint(tcyc)), &sn, &cs);
     return make_double2(am * cs, am * sn);
