@@ -81,7 +81,8 @@ def dftR(v, S):
         return dft16(v, S)
     k = np.arange(R)
     F = np.exp(-S * 2j * np.pi * np.outer(k, k) / R)       # the small butterflies are plain DFTs (dft2p/dft4/dft8 unchanged from round 1)
-    return np.tensordot(F, np.array(v), axes=(1, 0))
+    v = np.array(v)
+    return np.tensordot(F.astype(v.dtype), v, axes=(1, 0))
 
 
 def twiddle_powers(v, w1, conj):
@@ -116,8 +117,8 @@ def czt_row_emulated(x, Hf, lg):
     L = 1 << lg
     T, NREG, RT = L // 16, nreg(lg), turn_radix(lg)
     NB, NS = 16 // RT, L // RT
-    tw = roots(lg)
-    X = np.full(L + L // 16 + 1, np.nan, complex)
+    tw = roots(lg).astype(x.dtype)                      # the complex64 build reads the same roots rounded once (g_twf)
+    X = np.full(L + L // 16 + 1, np.nan, x.dtype)
     t = np.arange(T)
     s = np.arange(16)[:, None]
     v = dft16(x[t[None, :] + s * T], 1)
@@ -152,7 +153,7 @@ def czt_row_emulated(x, Hf, lg):
         X[:] = np.nan
         X[slot(t[None, :] + s * T)] = v
     v = dft16(X[(17 * t)[None, :] + s], -1)
-    y = np.empty(L, complex)
+    y = np.empty(L, x.dtype)
     y[t[None, :] + s * T] = v
     return y
 
@@ -258,3 +259,68 @@ def test_chirpz_equals_oracle_dft2(m, n, M, N, alpha, shift, offset):
     F = np.array([chirpz_axis(G[:, v], alpha[0], x0r, y0r, M, -1.0, lg_for(m, M)) for v in range(N)]).T      # stage B
     F *= np.sqrt(abs(alpha[0] * alpha[1]))
     assert np.max(np.abs(F - want)) <= 1e-10 * np.max(np.abs(want))
+
+
+@pytest.mark.parametrize("lg", [9, 11, 13])
+def test_complex64_build_accuracy(lg):
+    """The FP32 build of the row transform (complex64 mode): complex64 data and twiddles, the chirp filter H built in float64
+    and rounded once.  Peak-normalised error of the convolution against float64 stays ~1e-6, well inside the 1e-5 gate."""
+    L = 1 << lg
+    rng = np.random.default_rng(lg)
+    x = np.zeros(L, complex)
+    x[:L // 2 - 3] = rng.normal(size=L // 2 - 3) + 1j * rng.normal(size=L // 2 - 3)
+    h = np.exp(1j * np.pi * 0.37e-3 * (np.arange(L) - L / 2) ** 2)            # a chirp, like the real filter
+    Hf = np.fft.fft(h)
+    want = np.fft.ifft(np.fft.fft(x) * Hf)
+    got = czt_row_emulated(x.astype(np.complex64), Hf.astype(np.complex64), lg)
+    assert got.dtype == np.complex64
+    err = np.max(np.abs(got / L - want)) / np.max(np.abs(want))
+    assert err <= 3e-6, err
+
+
+def dft16_pruned(v, S, in8=False, out8=False):
+    """the IN8 / OUT8 forms of the kernel's dft16: zero upper half of the inputs not read, only outputs 0..7 formed"""
+    v = [np.array(x) for x in v]
+    for n2 in range(4):
+        if in8:
+            x0, x1 = v[n2], v[4 + n2]
+            m = mul_mi(x1, S)
+            v[n2], v[4 + n2], v[8 + n2], v[12 + n2] = x0 + x1, x0 + m, x0 - x1, x0 - m
+        else:
+            v[n2], v[4 + n2], v[8 + n2], v[12 + n2] = dft4(v[n2], v[4 + n2], v[8 + n2], v[12 + n2], S)
+    v[5] = mul_root(v[5], C1, S1, S)
+    v[6] = mul_root(v[6], H, H, S)
+    v[7] = mul_root(v[7], S1, C1, S)
+    v[9] = mul_root(v[9], H, H, S)
+    v[10] = mul_mi(v[10], S)
+    v[11] = mul_root(v[11], -H, H, S)
+    v[13] = mul_root(v[13], S1, C1, S)
+    v[14] = mul_root(v[14], -H, H, S)
+    v[15] = mul_root(v[15], -C1, -S1, S)
+    if not out8:
+        return dft16_tail(v, S)
+    lo = [(v[4 * k1] + v[4 * k1 + 2]) + (v[4 * k1 + 1] + v[4 * k1 + 3]) for k1 in range(4)]
+    hi = [(v[4 * k1] - v[4 * k1 + 2]) + mul_mi(v[4 * k1 + 1] - v[4 * k1 + 3], S) for k1 in range(4)]
+    return np.array(lo + hi)
+
+
+def dft16_tail(v, S):
+    for k1 in range(4):
+        v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3] = dft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3], S)
+    for a in range(4):
+        for b in range(a + 1, 4):
+            v[4 * a + b], v[4 * b + a] = v[4 * b + a], v[4 * a + b]
+    return np.array(v)
+
+
+@pytest.mark.parametrize("S", [1, -1])
+def test_pruned_butterflies_of_the_half_length_path(S):
+    rng = np.random.default_rng(7)
+    x = rng.normal(size=(16, 6)) + 1j * rng.normal(size=(16, 6))
+    full = dft16(x, S)
+    assert np.allclose(dft16_pruned(x, S, out8=True), full[:8], atol=1e-13)
+    xz = x.copy()
+    xz[8:] = 0
+    garbage = x.copy()
+    garbage[8:] = np.nan                                # IN8 must not read the upper half
+    assert np.allclose(dft16_pruned(garbage, S, in8=True), dft16(xz, S), atol=1e-13)
