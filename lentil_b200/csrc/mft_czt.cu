@@ -132,7 +132,7 @@ __device__ __forceinline__ const V2 *tw_table(int lg) { return g_tw[lg - MIN_LOG
 __device__ __forceinline__ V2 phasor(double am, double op, double, double inv_lam) {
     const double tcyc = op * inv_lam;
     double sn, cs;
-    sincospi(2.0 * (tcyc - rint(tcyc)), &sn, &cs);
+    cis_unit(tcyc - rint(tcyc), cs, sn);
     return make_double2(am * cs, am * sn);
 }
 #include "mft_czt_body.cuh"

@@ -91,7 +91,7 @@ __device__ __forceinline__ double2 pupil_phasor(const FoldDesc &d, int i, int c)
     if (a == 0.0) return make_double2(0.0, 0.0);
     const double tcyc = d.opd[pix] / d.wavelength;      // phase in cycles, reduced exactly
     double sn, cs;
-    sincospi(2.0 * (tcyc - rint(tcyc)), &sn, &cs);
+    cis_unit(tcyc - rint(tcyc), cs, sn);
     return make_double2(a * cs, a * sn);
 }
 

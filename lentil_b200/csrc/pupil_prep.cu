@@ -52,7 +52,7 @@ pupil_prep_kernel(const double *__restrict__ amp, const double *__restrict__ opd
                 dst[(long long)l * lam_stride] = make_float2(af * c, af * s);
             } else {
                 double s, c;
-                sincospi(2.0 * r, &s, &c);
+                cis_unit(r, c, s);
                 dst[(long long)l * lam_stride] = make_cplx<CT>(a * c, a * s);
             }
         }

@@ -258,7 +258,6 @@ class Plane(_PlaneBase):
                 mk8 = (mk > 0).astype(np.uint8)
             mk_dev = device.to_dev(mk8)
         ops['amp'] = device.to_dev(amp if amp.shape == shape else np.broadcast_to(amp, shape), dtype=np.float64)
-        ops['opd'] = device.to_dev(opd if opd.shape == shape else np.broadcast_to(opd, shape), dtype=np.float64)
         ops['mask'] = mk_dev if use_mask else None
         # the uploaded 0/1 mask cube itself, whether or not the phasor needs it (a scalar amplitude is not masked, but
         # fit_tilt still fits over the mask: lentil/plane.py:522-562)
@@ -271,7 +270,13 @@ class Plane(_PlaneBase):
             src, is_f64, nonzero = (ops['amp'], 1, 1) if mk_dev is None else (mk_dev, 0, 0)
             _lib.check(_lib.lib().lfd_mask_bbox(src.data_ptr(), is_f64, nonzero, shape[0], shape[1], nseg,
                                                 bb.data_ptr(), device.stream_ptr()), "lfd_mask_bbox")
-            bb = bb.cpu().numpy().reshape(nseg, 4)
+            # the OPD upload is queued behind the bounding-box read-back, so that it overlaps the host-side planning
+            # that follows instead of delaying the (synchronous) read-back
+            bb_host = bb.cpu()
+            ops['opd'] = device.to_dev(opd if opd.shape == shape else np.broadcast_to(opd, shape), dtype=np.float64)
+            bb = bb_host.numpy().reshape(nseg, 4)
+        if 'opd' not in ops:
+            ops['opd'] = device.to_dev(opd if opd.shape == shape else np.broadcast_to(opd, shape), dtype=np.float64)
         if np.any(bb[:, 1] < 0):
             raise IndexError('mask plane without any data: cannot find its boundary')   # as np.where(...)[0][[0,-1]]
         slices = [np.s_[int(b[0]):int(b[1]) + 1, int(b[2]):int(b[3]) + 1] for b in bb]
