@@ -1,5 +1,5 @@
 import cProfile, pstats, sys, os
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/scripts")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "scripts"))
 import numpy as np, torch
 import lentil_b200 as lentil, bench
 w = bench.WORKLOAD
