@@ -136,9 +136,12 @@ __device__ __forceinline__ void turn(V2 *X, const V2 *hv, int t, int q, V2 w1) {
 // and the load latency overlaps the barrier wait instead of the arithmetic.
 // HALF: n_in <= L / 2 and n_out <= L / 2 (the usual case: L is the power of two above n_in + n_out): the loader fills only
 // v[0..7], the first butterfly skips the zero half, the last one computes only the wanted half, the store writes v[0..7].
-template <int LOG2L, int ROWS, int NBUF, bool HALF, class Load16, class Store16>
+// `after_first_barrier()` runs once, right after the first barrier of the row (every thread has consumed its inputs by then):
+// the kernel uses it to start the asynchronous copy of the NEXT unit's input rows into the staging buffer.
+template <int LOG2L, int ROWS, int NBUF, bool HALF, class Load16, class Store16, class Hook>
 __device__ __forceinline__ void czt_row(V2 *&X, V2 *&Y, int t, const Load16 &load16, const V2 *__restrict__ H,
-                                        const V2 *__restrict__ post, int nout, const Store16 &store16) {
+                                        const V2 *__restrict__ post, int nout, const Store16 &store16,
+                                        const Hook &after_first_barrier) {
     constexpr int L = 1 << LOG2L, T = L / 16, NREG = nreg(LOG2L), RT = turn_radix(LOG2L), NB = 16 / RT, NS = L / RT;
     const V2 *__restrict__ tw = tw_table(LOG2L);
     const std::integral_constant<bool, HALF> half_tag;
@@ -153,6 +156,7 @@ __device__ __forceinline__ void czt_row(V2 *&X, V2 *&Y, int t, const Load16 &loa
         const int k = t & (Ns - 1), j0 = (t - k) * 16 + k;
         const V2 w1 = tw[tw_offset(p) + k];
         __syncthreads();
+        if (p == 1) after_first_barrier();
 #pragma unroll
         for (int s = 0; s < 16; ++s) v[s] = X[slot<ROWS>(t + s * T)];
         twiddle_powers<16, false>(v, w1);
@@ -172,6 +176,7 @@ __device__ __forceinline__ void czt_row(V2 *&X, V2 *&Y, int t, const Load16 &loa
 #pragma unroll
         for (int e = 0; e < HN; ++e) hv[e] = H[t + (e / RT) * T + (e % RT) * NS];
         __syncthreads();
+        if (NREG == 1) after_first_barrier();
 #pragma unroll
         for (int q = 0; q < NB; ++q) {
 #pragma unroll
@@ -245,6 +250,23 @@ czt_stage_kernel(const Plane *__restrict__ descs, const int *__restrict__ starts
 #endif
     if (w0 >= w1) return;
     __shared__ Plane sd;                 // the plane this CTA is working on
+    // Input staging (STG): while a unit is being transformed, the copy engine brings the NEXT unit's input rows into shared
+    // memory (cp.async.bulk, completion on an mbarrier), so the first pass of the next unit reads shared memory instead of
+    // waiting for HBM / L2.  One staging buffer suffices: it is refilled right after the first barrier of a row (all reads
+    // of it are done) and has the rest of the row (~10 us) to arrive.  Region of row c: STG_REGION bytes (one complex row, or
+    // the amp row followed by the opd row); the copy starts at the 16-byte boundary below the row, s_sh holds the shifts.
+    constexpr bool STG = LFD_CZT_STAGING && LOG2L >= LFD_CZT_STAGING_MINLG;
+    constexpr int STG_REGION = (L / 2 + 4) * 16;
+    unsigned char *stg = sm_raw + (size_t)NBUF * ROWS * (L + L / 16) * sizeof(V2);
+    __shared__ Plane sdn;                // the plane after it (the successor of a unit usually lies there)
+    __shared__ __align__(8) uint64_t stg_bar;
+    __shared__ int s_staged, s_sh[2 * ROWS];
+    uint32_t stg_phase = 0;
+    int pend2 = 0;                       // first unit after the NEXT plane
+    if (STG) {
+        if (threadIdx.x == 0) { mbar_init(&stg_bar, 1); mbar_fence_init(); s_staged = 0; }
+        __syncthreads();
+    }
     int plane = 0, cur = -1;
     {   // last plane whose first unit is <= w0 (planes of another length own no units: their start equals the next one's)
         int lo = 0, hi = count;
@@ -260,8 +282,14 @@ czt_stage_kernel(const Plane *__restrict__ descs, const int *__restrict__ starts
             const unsigned long long *g = reinterpret_cast<const unsigned long long *>(descs + plane);
             unsigned long long *sdw = reinterpret_cast<unsigned long long *>(&sd);
             for (int i = threadIdx.x; i < (int)(sizeof(Plane) / 8); i += NT) sdw[i] = g[i];
+            if (STG && plane + 1 < count) {
+                const unsigned long long *gn = reinterpret_cast<const unsigned long long *>(descs + plane + 1);
+                unsigned long long *snw = reinterpret_cast<unsigned long long *>(&sdn);
+                for (int i = threadIdx.x; i < (int)(sizeof(Plane) / 8); i += NT) snw[i] = gn[i];
+            }
             __syncthreads();
             cur = plane;
+            pend2 = (STG && plane + 1 < count) ? starts[plane + 2] : pend;
         }
         const Plane &d = sd;
         const int nrows = STAGE_A ? d.m : d.N;
@@ -272,7 +300,64 @@ czt_stage_kernel(const Plane *__restrict__ descs, const int *__restrict__ starts
         const V2 *__restrict__ post = (const V2 *)(STAGE_A ? d.postA : d.postB);
         const V2 *__restrict__ H = (const V2 *)(STAGE_A ? d.HA : d.HB);
         const Plane *dp = &d;
-        if (LFD_CZT_L2PRE && LOG2L <= LFD_CZT_PRE_MAXLG && w + stride < w1 && w + stride < pend && row + stride * ROWS < nrows) {   // next unit in the same plane: pull its input rows into L2 now
+        // was this unit's input staged by the previous iteration?  (uniform: written by thread 0 before the last barrier)
+        const bool staged = STG && s_staged != 0;
+        int sh0 = 0, sh1 = 0;
+        if (staged) {
+            sh0 = s_sh[2 * c]; sh1 = s_sh[2 * c + 1];
+            mbar_wait(&stg_bar, stg_phase);
+            stg_phase ^= 1;
+        }
+        const unsigned char *stg_row = stg + c * STG_REGION;
+        // where the next unit of this CTA lies (thread 0 issues its copies from the hook below)
+        const int wn = w + stride;
+        const bool next_here = wn < w1 && wn < pend, next_there = wn < w1 && wn >= pend && wn < pend2;
+        const Plane *np_ = next_here ? &sd : &sdn;
+        const int nrow0 = next_here ? (wn - pbeg) * ROWS : (wn - pend) * ROWS;
+        auto hook = [=]() {
+            if (!STG || threadIdx.x != 0) return;
+            int ok = 0;
+            const int nnin = STAGE_A ? np_->n : np_->m, nnrows = STAGE_A ? np_->m : np_->N;
+            const int nnout = STAGE_A ? np_->N : np_->M;
+            if ((next_here || next_there) && (STAGE_A ? np_->logLA : np_->logLB) == LOG2L && nnin <= L / 2 && nnout <= L / 2) {
+                const bool fusedn = STAGE_A && np_->amp != nullptr;
+                const int es = fusedn ? 8 : (int)sizeof(V2);
+                uint32_t total = 0;
+                bool safe = true;
+                const unsigned char *src[2 * ROWS];
+                uint32_t nb[2 * ROWS];
+#pragma unroll
+                for (int cc = 0; cc < ROWS; ++cc) {
+                    const long long r = nrow0 + cc;
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        src[2 * cc + a] = nullptr; nb[2 * cc + a] = 0;
+                        if (r >= nnrows || (a == 1 && !fusedn)) continue;
+                        const unsigned char *b0 = fusedn ? (const unsigned char *)(a ? np_->opd : np_->amp) + ((r + np_->pr0) * np_->pld + np_->pc0) * 8
+                                                : (STAGE_A ? (const unsigned char *)np_->f + r * np_->ldf * es
+                                                           : (const unsigned char *)np_->Gt + r * np_->mpad * es);
+                        const uint32_t sh = (uint32_t)((uintptr_t)b0 & 15);
+                        const uint32_t bytes = (sh + (uint32_t)nnin * es + 15u) & ~15u;
+                        // never read past the end of the plane's last row: the tail beyond a row is the next row (or padding)
+                        if (r == nnrows - 1 && ((sh + (uint32_t)nnin * es) & 15u) != 0 && STAGE_A) safe = false;
+                        src[2 * cc + a] = b0 - sh; nb[2 * cc + a] = bytes;
+                        s_sh[2 * cc + a] = (int)sh;
+                        total += bytes;
+                    }
+                }
+                if (safe && total > 0) {
+                    mbar_expect_tx(&stg_bar, total);
+#pragma unroll
+                    for (int cc = 0; cc < ROWS; ++cc)
+#pragma unroll
+                        for (int a = 0; a < 2; ++a)
+                            if (nb[2 * cc + a]) bulk_g2s(stg + cc * STG_REGION + a * (STG_REGION / 2), src[2 * cc + a], nb[2 * cc + a], &stg_bar);
+                    ok = 1;
+                }
+            }
+            s_staged = ok;
+        };
+        if (!STG && LFD_CZT_L2PRE && LOG2L <= LFD_CZT_PRE_MAXLG && w + stride < w1 && w + stride < pend && row + stride * ROWS < nrows) {   // next unit in the same plane: pull its input rows into L2 now
             const long long nrow = row + stride * ROWS;
 #pragma unroll
             for (int sI = 0; sI < 16; sI += 2) {                         // one prefetch per 32-byte sector pair of this thread's elements
@@ -307,12 +392,15 @@ czt_stage_kernel(const Plane *__restrict__ descs, const int *__restrict__ starts
                     double am[8], op[8];
                     const long long base = (long long)(dp->pr0 + row) * dp->pld + dp->pc0;
                     const unsigned char *mk = dp->mask;
+                    // the row's amplitude and OPD: staged in shared memory by the previous unit, or straight from global memory
+                    const double *sa = staged ? (const double *)(stg_row + sh0) : dp->amp + base;
+                    const double *so = staged ? (const double *)(stg_row + STG_REGION / 2 + sh1) : dp->opd + base;
                     if (all_in) {
 #pragma unroll
                         for (int s = 0; s < 8; ++s) {
                             const int i = t + (hf * 8 + s) * T;
-                            am[s] = dp->amp[base + i];
-                            op[s] = dp->opd[base + i];
+                            am[s] = sa[i];
+                            op[s] = so[i];
                             pr[s] = pre[i];
                         }
                         if (mk != nullptr) {
@@ -325,8 +413,8 @@ czt_stage_kernel(const Plane *__restrict__ descs, const int *__restrict__ starts
                         for (int s = 0; s < 8; ++s) {
                             const int i = t + (hf * 8 + s) * T;
                             const bool in = rv && i < nin;
-                            am[s] = in ? dp->amp[base + i] : 0.0;
-                            op[s] = in ? dp->opd[base + i] : 0.0;
+                            am[s] = in ? sa[i] : 0.0;
+                            op[s] = in ? so[i] : 0.0;
                             pr[s] = in ? pre[i] : mk2((RL)0, (RL)0);
                             if (in && mk != nullptr && mk[base + i] == 0) am[s] = 0.0;
                         }
@@ -339,7 +427,8 @@ czt_stage_kernel(const Plane *__restrict__ descs, const int *__restrict__ starts
                         v[hf * 8 + s] = cmul(x, pr[s]);
                     }
                 } else {
-                    const V2 *src = STAGE_A ? (const V2 *)dp->f + (long long)row * dp->ldf : (const V2 *)dp->Gt + (long long)row * dp->mpad;
+                    const V2 *src = staged ? (const V2 *)(stg_row + sh0)
+                                           : (STAGE_A ? (const V2 *)dp->f + (long long)row * dp->ldf : (const V2 *)dp->Gt + (long long)row * dp->mpad);
                     V2 x[8];
                     if (all_in) {
 #pragma unroll
@@ -380,8 +469,8 @@ czt_stage_kernel(const Plane *__restrict__ descs, const int *__restrict__ starts
                     if (rv && i < nout) Gt[(long long)i * mpad] = v[s];
                 }
             };
-            if (half) czt_row<LOG2L, ROWS, NBUF, true>(X, Y, t, load, H, post, nout, store);
-            else czt_row<LOG2L, ROWS, NBUF, false>(X, Y, t, load, H, post, nout, store);
+            if (half) czt_row<LOG2L, ROWS, NBUF, true>(X, Y, t, load, H, post, nout, store, hook);
+            else czt_row<LOG2L, ROWS, NBUF, false>(X, Y, t, load, H, post, nout, store, hook);
         } else if (dp->intensity) {
             double *out = (double *)dp->out + row; const long long ldo = dp->ldo;
             auto store = [=](V2 (&v)[16], auto half_tag) {
@@ -397,8 +486,8 @@ czt_stage_kernel(const Plane *__restrict__ descs, const int *__restrict__ starts
                     if (rv && i < nout) out[(long long)i * ldo] = (double)v[s].x * (double)v[s].x + (double)v[s].y * (double)v[s].y;
                 }
             };
-            if (half) czt_row<LOG2L, ROWS, NBUF, true>(X, Y, t, load, H, post, nout, store);
-            else czt_row<LOG2L, ROWS, NBUF, false>(X, Y, t, load, H, post, nout, store);
+            if (half) czt_row<LOG2L, ROWS, NBUF, true>(X, Y, t, load, H, post, nout, store, hook);
+            else czt_row<LOG2L, ROWS, NBUF, false>(X, Y, t, load, H, post, nout, store, hook);
         } else {
             V2 *out = (V2 *)dp->out + row; const long long ldo = dp->ldo;
             auto store = [=](V2 (&v)[16], auto half_tag) {
@@ -414,8 +503,8 @@ czt_stage_kernel(const Plane *__restrict__ descs, const int *__restrict__ starts
                     if (rv && i < nout) out[(long long)i * ldo] = v[s];
                 }
             };
-            if (half) czt_row<LOG2L, ROWS, NBUF, true>(X, Y, t, load, H, post, nout, store);
-            else czt_row<LOG2L, ROWS, NBUF, false>(X, Y, t, load, H, post, nout, store);
+            if (half) czt_row<LOG2L, ROWS, NBUF, true>(X, Y, t, load, H, post, nout, store, hook);
+            else czt_row<LOG2L, ROWS, NBUF, false>(X, Y, t, load, H, post, nout, store, hook);
         }
     }
 }
