@@ -500,14 +500,15 @@ def run_ours(args):
             "bound": "fp64",
             "bound_detail": "FP64 pipe of the SM (DADD/DMUL/DFMA; the same unit executes DMMA), second limiter shared-memory "
                             "bandwidth; not HBM-bound and no tensor-core instruction is issued. ncu: profiles/",
-            "kernel": "czt_stage_kernel<11,true>+<11,false> (K2a, chirp-z execution: per row FFT_2048 -> x FFT(chirp) -> "
+            "kernel": "czt::f64::czt_stage_kernel<11,true>+<11,false> (K2a, chirp-z execution: per row FFT_2048 -> x FFT(chirp) -> "
                       "IFFT_2048 in shared memory, radix-16 passes; one launch = tables + row stage + column stage of the batch)",
             "achieved": executed, "peak": peak, "unit": "TFLOP/s", "frac": executed / peak if executed else None,
             "traffic": None,
             "traffic_note": "not measured in this run; the ncu --set full capture committed under profiles/ is quoted in traffic_ncu",
             "traffic_ncu": ncu_traffic,
             "flops_per_launch": mft_exec / max(mft_launches, 1),
-            "flops_model": "EXECUTED flops: per row transform 2 FFTs of length L (5 L log2 L each) + 6 (L + n_in + n_out) for "
+            "flops_model": "EXECUTED flops: per row transform 2 FFTs of length L (5 L log2 L each, the textbook count; the kernel's "
+                           "half-length pruning of the first / last butterfly executes ~3 % fewer) + 6 (L + n_in + n_out) for "
                            "the three point-wise products; rows = m + N per plane; L = 2048",
             "avg_launch_ms": mft_ms / max(mft_launches, 1), "launches": mft_launches,
             "share_of_step": mft_ms / ms,
