@@ -307,6 +307,8 @@ def run_ours(args):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = device.set_device(local)
+    cpus_before = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa_cpus = device.bind_cpu_affinity(local) if world > 1 else None     # one process per GPU: stay on the GPU's NUMA node
     lib = _lib.lib()
     w = WORKLOAD
     nlam_total = w["nlam"] * world
@@ -455,8 +457,12 @@ def run_ours(args):
         got = lentil.propagate_dft_batch(pupil, wls[sub], w["du"], shape, oversample=w["oversample"], weights=wts[sub],
                                          distributed=True)
         if rank == 0:
+            if numa_cpus and cpus_before:
+                os.sched_setaffinity(0, cpus_before)
             _limit_threads(os.cpu_count())
             ref, _ = cpu_reference_psf(amp, opd, wls[sub], wts[sub])
+            if numa_cpus:
+                os.sched_setaffinity(0, numa_cpus)
             parity_distributed = {"peak_normalised_error": float(np.max(np.abs(got - ref)) / np.max(ref)),
                                   "wavelengths": int(len(sub)), "ranks": world,
                                   "what": "propagate_dft_batch(distributed=True) over all ranks (NCCL all-reduce) vs the CPU "
@@ -558,6 +564,8 @@ def run_ours(args):
           "note": "one FP64 sincospi per element: the FP64 pipe, not HBM, limits this kernel"}
 
     # ---- CPU baseline (bounded sample of the same workload) -------------------------------------------
+    if numa_cpus and cpus_before:
+        os.sched_setaffinity(0, cpus_before)               # the CPU legs may use every host core again
     _limit_threads(os.cpu_count())
     cpu_value, cpu_planes, cpu_s, kind = time_cpu(amp, opd, wls[:w["nlam"]], wts[:w["nlam"]],
                                                   budget_s=12.0 if world == 1 else 3.0, max_planes=40)
@@ -581,7 +589,8 @@ def run_ours(args):
         "data": "synthetic", "config": workload_config(world),
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "planes/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "api": "lentil_b200.propagate_dft_batch(Pupil(numpy...)) -> numpy"},
+                "d2h_bytes_per_step": int(d2h), "api": "lentil_b200.propagate_dft_batch(Pupil(numpy...)) -> numpy",
+                "cpu_affinity": (f"{len(numa_cpus)} cores local to the GPU (NVML)" if numa_cpus else "unchanged")},
         "roofline": roofline,
         "roofline_tensor": roofline_tensor,
         "k1": k1, "k3": k3,

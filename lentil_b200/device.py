@@ -39,6 +39,28 @@ def set_device(index):
     return _device
 
 
+def bind_cpu_affinity(index=None):
+    """Pin this process to the CPU cores NVML reports as local to GPU `index` (its NUMA node), so that pinned staging
+    buffers are first-touched next to the GPU's PCIe root and host<->device copies do not cross sockets.  One process per
+    GPU deployments (torchrun) call it once before allocating pinned memory.  Returns the CPU set, or None when NVML or
+    sched_setaffinity is unavailable (nothing is changed then)."""
+    try:
+        import pynvml
+        idx = device().index if index is None else int(index)
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or None
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 

@@ -372,3 +372,36 @@ def test_k2a_execution_choice_and_workspace_are_host_decisions():
         assert L.lfd_set_mft_variant(7) != 0 and b"unknown MFT variant" in L.lfd_last_error()
     finally:
         L.lfd_set_mft_variant(saved)
+
+
+def test_bind_cpu_affinity_is_harmless_without_nvml():
+    # on a box without a GPU / NVML the helper changes nothing and says so
+    import os
+    from lentil_b200 import device
+    before = os.sched_getaffinity(0)
+    got = device.bind_cpu_affinity(0)
+    assert got is None or isinstance(got, set)
+    if got is None:
+        assert os.sched_getaffinity(0) == before
+    else:
+        os.sched_setaffinity(0, before)
+
+
+def test_execution_names_map_to_the_descriptor_field():
+    from lentil_b200 import fourier, _lib
+    assert [fourier.execution_code(k) for k in (None, 'direct', 'folded', 'czt', 'auto')] == [0, 1, 2, 3, 4]
+    with pytest.raises(ValueError):
+        fourier.execution_code('fft')
+    # a per-call choice overrides the process default in the host-side resolver (no device needed)
+    L = _lib.lib()
+    d = (_lib.MftDesc * 1)()
+    d[0].m = d[0].n = 1001
+    d[0].M = d[0].N = 1024
+    assert L.lfd_mft_execution(d, 1) == 2                       # default AUTO -> chirp-z
+    d[0].execution = 2
+    assert L.lfd_mft_execution(d, 1) == 1                       # forced folded (1 + LFD_MFT_FOLDED)
+    assert L.lfd_mft_c64_execution(d, 1) == 1                   # complex64: tcgen05 form
+    d[0].execution = 4
+    assert L.lfd_mft_execution(d, 1) == 2 and L.lfd_mft_c64_execution(d, 1) == 2
+    d[0].m = 9000                                               # 10023 -> beyond the 8192-point kernel
+    assert L.lfd_mft_execution(d, 1) == 1 and L.lfd_mft_c64_execution(d, 1) == 1
