@@ -441,3 +441,33 @@ def test_fourier_level_patch_reroutes_a_numpy_propagation(golden):
     assert oc.dft2 is not lentil.fourier.dft2
     assert lentil.device.launch_count() - n0 >= len(d["A_wls"])      # one K2a launch group per wavelength
     assert peak_err(got, ref) <= TOL64 and peak_err(got, d["A_img"]) <= TOL64
+
+
+def test_batch_normalises_device_inputs_and_validates_out():
+    # caller-supplied device tensors are normalised (dtype / layout) instead of being read as dense float64
+    import torch
+    rng = np.random.default_rng(21)
+    mask = synth.circle((96, 96), 45)
+    amp = synth.normalize_power(mask)
+    opds = np.stack([synth.zernike_opd(mask, rng.normal(size=8) * 20e-9, first=4) for _ in range(3)])
+    dx, z, du = 1 / 90, 20.0, 5e-6
+    wls, wts = [6e-7, 7e-7], [0.5, 0.5]
+    p = lentil.Pupil(amplitude=amp, opd=np.zeros((96, 96)), pixelscale=dx, focal_length=z)
+    want = lentil.propagate_dft_batch(p, wls, du, (48, 48), oversample=2, weights=wts, opds=opds)
+    dev = lentil.device.device()
+    f32 = torch.from_numpy(opds).to(dev, torch.float32)                         # wrong dtype
+    got = lentil.propagate_dft_batch(p, wls, du, (48, 48), oversample=2, weights=wts, opds=f32)
+    assert peak_err(got, want) <= 1e-5                                           # float32 OPDs: rounded inputs, not garbage
+    wide = torch.zeros(3, 96, 200, dtype=torch.float64, device=dev)
+    wide[:, :, :96] = torch.from_numpy(opds).to(dev)
+    got = lentil.propagate_dft_batch(p, wls, du, (48, 48), oversample=2, weights=wts, opds=wide[:, :, :96])   # non-contiguous view
+    assert peak_err(got, want) <= 1e-14
+    # out: accumulate-into semantics, and rejection of buffers the kernels could not address
+    out = torch.full((3, 96, 96), 2.0, dtype=torch.float64, device=dev)
+    res = lentil.propagate_dft_batch(p, wls, du, (48, 48), oversample=2, weights=wts, opds=opds, out=out, return_device=True)
+    assert res.data_ptr() == out.data_ptr()
+    assert peak_err(lentil.device.to_host(out) - 2.0, want) <= 1e-13
+    for bad in (torch.zeros(3, 96, 96, dtype=torch.float32, device=dev), torch.zeros(3, 96, 192, dtype=torch.float64, device=dev)[:, :, ::2],
+                torch.zeros(2, 96, 96, dtype=torch.float64, device=dev), np.zeros((3, 96, 96))):
+        with pytest.raises(ValueError):
+            lentil.propagate_dft_batch(p, wls, du, (48, 48), oversample=2, weights=wts, opds=opds, out=bad)
