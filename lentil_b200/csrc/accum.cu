@@ -86,7 +86,10 @@ accum_kernel(const lfd_window *__restrict__ wins, int nwin, double *__restrict__
 // Pure HBM streaming: two pixels per thread (16-byte loads), eight planes in flight per thread, window pointers and
 // weights in shared memory.  The sum runs over v in the same order and with the same contraction as accum_kernel, so
 // both paths give bit-identical images.
+// FIELDS: the windows are dense full-frame complex128 fields, one per wavefront (nothing to merge coherently): out += sum_v w_v
+// |E_v|^2, one pixel per thread — what the per-wavelength drop-in loop (Wavefront.insert of a single-Field wavefront) produces.
 constexpr int FULL_CHUNK = 512;      // windows per launch of the fast path (one accumulation per pixel, as in accum_kernel); more -> generic path
+template <bool FIELDS>
 __global__ void __launch_bounds__(256)
 accum_full_kernel(const lfd_window *__restrict__ wins, int nwin, double *__restrict__ out, long long npairs) {
     __shared__ const double2 *sE[FULL_CHUNK];
@@ -101,6 +104,23 @@ accum_full_kernel(const lfd_window *__restrict__ wins, int nwin, double *__restr
         }
         __syncthreads();
         for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < npairs; e += stride) {
+            if constexpr (FIELDS) {
+                double a = 0.0;
+                int v = 0;
+                for (; v + 8 <= nv; v += 8) {
+                    double2 x[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) x[k] = __ldcs(sE[v + k] + e);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) a += sw[v + k] * (x[k].x * x[k].x + x[k].y * x[k].y);
+                }
+                for (; v < nv; ++v) {
+                    const double2 x = __ldcs(sE[v] + e);
+                    a += sw[v] * (x.x * x.x + x.y * x.y);
+                }
+                out[e] += a;
+                continue;
+            }
             double a0 = 0.0, a1 = 0.0;
             int v = 0;
             for (; v + 8 <= nv; v += 8) {
@@ -121,11 +141,14 @@ accum_full_kernel(const lfd_window *__restrict__ wins, int nwin, double *__restr
     }
 }
 
-static bool all_full_frame_intensity(const lfd_window *wins, int nwin, const void *out, int H, int W, int64_t ldo) {
-    if (nwin > FULL_CHUNK || ldo != W || (((long long)H * W) & 1) || ((uintptr_t)out & 15)) return false;
+// kind 2: float64 intensity planes; kind 0: complex128 fields, every window its own wavefront (strictly increasing groups)
+static bool all_full_frame(const lfd_window *wins, int nwin, const void *out, int H, int W, int64_t ldo, int kind) {
+    if (nwin > FULL_CHUNK || ldo != W || ((uintptr_t)out & 15)) return false;
+    if (kind == 2 && (((long long)H * W) & 1)) return false;
     for (int v = 0; v < nwin; ++v) {
         const lfd_window &w = wins[v];
-        if (w.c64 != 2 || w.r0 != 0 || w.c0 != 0 || w.h != H || w.w != W || w.ld != W || ((uintptr_t)w.E & 15)) return false;
+        if (w.c64 != kind || w.r0 != 0 || w.c0 != 0 || w.h != H || w.w != W || w.ld != W || ((uintptr_t)w.E & 15)) return false;
+        if (kind == 0 && v > 0 && w.group <= wins[v - 1].group) return false;
     }
     return true;
 }
@@ -147,12 +170,15 @@ static int launch_accum(bool intensity, const lfd_window *wins, int32_t nwin, vo
     }
     LFD_CUDA_OK(cudaMemcpyAsync(scratch, wins, (size_t)nwin * sizeof(lfd_window),
                                 cudaMemcpyHostToDevice, stream));
-    if (intensity && all_full_frame_intensity(wins, nwin, out, H, W, ldo)) {
-        const long long npairs = (long long)H * W / 2;
-        long long blocks = (npairs + 255) / 256;
+    const bool planes = intensity && all_full_frame(wins, nwin, out, H, W, ldo, 2);
+    const bool fields = intensity && !planes && all_full_frame(wins, nwin, out, H, W, ldo, 0);
+    if (planes || fields) {
+        const long long nelem = planes ? (long long)H * W / 2 : (long long)H * W;
+        long long blocks = (nelem + 255) / 256;
         const long long cap = (long long)sm_or_default() * 8;
         if (blocks > cap) blocks = cap;
-        accum_full_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const lfd_window *)scratch, nwin, (double *)out, npairs);
+        if (planes) accum_full_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>((const lfd_window *)scratch, nwin, (double *)out, nelem);
+        else accum_full_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>((const lfd_window *)scratch, nwin, (double *)out, nelem);
         LFD_CUDA_OK(cudaGetLastError());
         count_launch();
         return 0;
