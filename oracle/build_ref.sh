@@ -4,7 +4,8 @@
 #
 # Used only as the checker / CPU baseline:
 #   * bench.py --impl reference and bench.py's cpu_baseline leg time it on the host cores (kind: "reference"),
-#   * tests/ import it to test lentil_b200.patch.enable() against the real package and to cross-check the oracle port.
+#   * tests/ import it to test lentil_b200.patch.enable() against the real package and to cross-check the oracle port,
+#     and run the reference's OWN test files (staged beside it) with its dft2 / idft2 rebound to the CUDA library.
 # Nothing under lentil_b200/ imports it.
 #
 # The copy is pinned: every file's sha256 must match oracle/ref_manifest.sha256 (written once with --pin from the
@@ -20,14 +21,16 @@ if [ ! -d "$SRC/lentil" ]; then
     if [ -d "$DST/lentil" ]; then echo "oracle/_ref: reference tree absent, keeping the staged copy"; exit 0; fi
     echo "oracle/_ref: no reference tree at $SRC and nothing staged" >&2; exit 1
 fi
+# the package and its own test-suite (tests/test_gpu_reference_own_tests.py runs the latter against the patched package)
+list_files() { (cd "$SRC" && find lentil tests -name '*.py' -type f | LC_ALL=C sort); }
 if [ "${1:-}" = "--pin" ]; then
-    (cd "$SRC" && find lentil -name '*.py' -type f | LC_ALL=C sort | xargs sha256sum) > "$MANIFEST"
+    (cd "$SRC" && list_files | xargs sha256sum) > "$MANIFEST"
     echo "pinned $(wc -l < "$MANIFEST") files"
 fi
 (cd "$SRC" && sha256sum --quiet -c "$MANIFEST")
 rm -rf "$DST"
 mkdir -p "$DST/lentil"
-(cd "$SRC" && find lentil -name '*.py' -type f | LC_ALL=C sort) | while read -r f; do
+list_files | while read -r f; do
     mkdir -p "$DST/$(dirname "$f")"
     cp "$SRC/$f" "$DST/$f"
 done
