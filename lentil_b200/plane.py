@@ -139,6 +139,44 @@ class _PlaneBase:
         self._frozen = False
         self._dev_cache = None
 
+    def rescale(self, scale):
+        """Rescale a plane by interpolation (lentil/plane.py:271-330): amplitude by 3rd-order splines divided by `scale`
+        (total power preserved), OPD by 3rd-order splines, mask by 0-order interpolation forced back to 0/1, pixelscale
+        divided by `scale`.  The interpolation is the device `rescale` (rescale.cu: B-spline prefilter + separable
+        evaluation, the scipy map_coordinates arithmetic of lentil/util.py:261-340)."""
+        from .detector import rescale as _rescale
+        plane = copy.deepcopy(self)
+        frozen = plane._frozen
+        plane._frozen = False
+        if np.ndim(plane.amplitude) > 1:
+            plane.amplitude = _rescale(np.asarray(plane.amplitude), scale=scale, shape=None, mask=None, order=3, mode='nearest',
+                                       unitary=False) / scale
+        if np.ndim(plane.opd) > 1:
+            plane.opd = _rescale(np.asarray(plane.opd), scale=scale, shape=None, mask=None, order=3, mode='nearest', unitary=False)
+        if plane._mask is not None:
+            m = np.asarray(plane._mask)
+            if m.ndim == 2:
+                m = _rescale(m, scale=scale, shape=None, mask=None, order=0, mode='constant', unitary=False)
+            else:
+                m = np.asarray([_rescale(k, scale=scale, shape=None, mask=None, order=0, mode='constant', unitary=False) for k in m])
+            m[np.nonzero(m)] = 1
+            plane._mask = m.astype(int)
+        if plane.pixelscale is not None:
+            ps = np.broadcast_to(plane.pixelscale, (2,))
+            plane._pixelscale = (ps[0] / scale, ps[1] / scale)
+        plane._frozen = frozen
+        plane._dev_cache = None
+        return plane
+
+    def resample(self, pixelscale):
+        """Resample a plane to another pixelscale (lentil/plane.py:332-367)."""
+        if self.pixelscale is None or not np.all(np.asarray(self.pixelscale)):
+            raise ValueError("can't resample Plane with pixelscale = ()")
+        ps = np.broadcast_to(self.pixelscale, (2,))
+        if ps[0] != ps[1]:
+            raise NotImplementedError("Can't resample non-uniformly sampled Plane")
+        return self.rescale(scale=ps[0] / pixelscale)
+
     def __deepcopy__(self, memo):
         new = self.__class__.__new__(self.__class__)
         memo[id(self)] = new
