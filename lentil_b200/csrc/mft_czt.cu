@@ -27,6 +27,16 @@
 //  * stage A transforms the rows of f (K1 can be fused: the phasor amp*mask*exp(2 pi i opd / lambda) is formed in the
 //    load, lentil/plane.py:502-507) and stores its result transposed, stage B transforms the rows of that (= the
 //    columns of the plane) and stores F, or |F|^2 as float64 when the caller only wants intensities.
+//  * work units (ROWS rows of a plane) are dealt round-robin over exact per-length unit tables (adjacent rows are written
+//    concurrently, so the scattered stores complete their lines in L2); planes of a batch whose row stage is the same
+//    computation (a grid of field points) share one stage-A result.
+//  * half-length fast path: when n_in and n_out both fit L / 2 (the usual case) the first butterfly skips its zero half, the
+//    last one forms only the wanted half, and interior threads load / store without predicates.
+//  * from L = 2048 up the NEXT unit's input rows are copied into a shared-memory staging buffer by the bulk-copy engine
+//    (cp.async.bulk + mbarrier) while the current unit computes; the pass twiddle, half of H and part of the post-chirp are
+//    fetched before the barrier that precedes their pass.
+//  * the same device code is compiled twice (mft_czt_body.cuh): complex128 / FP64, and complex64 / FP32 for the optional
+//    complex64 mode (tables still built in float64 and rounded once).
 //  * L <= 8192: one buffer of L complex128 (139 KB with padding) is the most that fits the 227 KB of an SM; longer
 //    transforms use the folded DMMA execution (the dispatcher in mft_c128.cu decides).
 #include "lfd_common.cuh"
