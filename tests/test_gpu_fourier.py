@@ -1,7 +1,6 @@
 """K2a parity: lentil_b200.fourier.dft2/idft2 (C ABI -> CUDA) against the oracle, the reference's
 golden vectors and the reference's own property tests (tests/test_fourier.py).  Tolerance: the
 FP64 gate of BASELINE.json, 1e-10 peak-normalised (observed ~1e-14)."""
-import ctypes as C
 
 import numpy as np
 import pytest
