@@ -12,8 +12,8 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["capi.cu", "mft_c128.cu", "mft_folded.cu", "mft_czt.cu", "mft_c64.cu", "pupil_prep.cu", "accum.cu", "fit_tilt.cu", "detector_ops.cu", "rescale.cu"]
-HEADERS = ["lfd_common.cuh", os.path.join(ROOT, "include", "lentil_b200.h")]
+SOURCES = ["capi.cu", "mft_c128.cu", "mft_folded.cu", "mft_czt.cu", "mft_czt_f32.cu", "mft_c64.cu", "pupil_prep.cu", "accum.cu", "fit_tilt.cu", "detector_ops.cu", "rescale.cu"]
+HEADERS = ["lfd_common.cuh", "mft_czt_common.cuh", "mft_czt_body.cuh", os.path.join(ROOT, "include", "lentil_b200.h")]
 LIB = os.path.join(os.path.dirname(HERE), "liblentil_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
 

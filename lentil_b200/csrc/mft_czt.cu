@@ -39,102 +39,16 @@
 //    complex64 mode (tables still built in float64 and rounded once).
 //  * L <= 8192: one buffer of L complex128 (139 KB with padding) is the most that fits the 227 KB of an SM; longer
 //    transforms use the folded DMMA execution (the dispatcher in mft_c128.cu decides).
-#include "lfd_common.cuh"
+#include "mft_czt_common.cuh"
 #include <map>
 #include <mutex>
 #include <tuple>
-#include <type_traits>
 
 namespace lfd {
 namespace czt {
 
-constexpr int MAX_LOG2L = 13, MIN_LOG2L = 6;
-// pass plan of a length: nreg radix-16 passes (the first of them has no twiddles), then the turn of radix 2 / 4 / 8 / 16
-__host__ __device__ constexpr int nreg(int lg) { return (lg - 1) / 4; }
-__host__ __device__ constexpr int turn_radix(int lg) { return 1 << (lg - 4 * nreg(lg)); }
-// Pass twiddles, one contiguous run per (FFT length, pass): pass p >= 1 has sub-transform length Ns = 16^p and reads
-// g_tw[lg][tw_offset(p) + k] = exp(-2 pi i k / (Ns R)), k = 0 .. Ns - 1 (R = 16, or the turn's radix for p = nreg).
-// Consecutive butterflies read consecutive entries.
-__host__ __device__ constexpr int tw_offset(int p) { return ((1 << (4 * p)) - 16) / 15; }
-constexpr int TW_PER_LEN = 4400;                 // 16 + 256 + 4096 = 4368 entries for the longest transform
 __device__ double2 g_tw[MAX_LOG2L - MIN_LOG2L + 1][TW_PER_LEN];
-__device__ float2 g_twf[MAX_LOG2L - MIN_LOG2L + 1][TW_PER_LEN];      // the same roots rounded once, for the complex64 build
-
-// rows per CTA and buffers per row, by length (measured, r02: profiles/r02_czt_variants.md): 128-thread CTAs up to
-// L = 1024 (ROWS * L = 2048), two rows (256 threads) at L = 2048, one row beyond.  LFD_CZT_ELEMS overrides ROWS * L.
-#ifndef LFD_CZT_ELEMS
-#define LFD_CZT_ELEMS 0
-#endif
-#ifndef LFD_CZT_NBUF
-#define LFD_CZT_NBUF 1
-#endif
-// tables fetched before the barrier that precedes their pass (registers are free there, but only so many of them)
-#ifndef LFD_CZT_HPRE
-#define LFD_CZT_HPRE 8        // how many of a thread's 16 values of H are fetched before the turn's barrier (0, 4, 8 or 16)
-#endif
-#ifndef LFD_CZT_PRE_MAXLG
-#define LFD_CZT_PRE_MAXLG 11  // ... all three prefetches only for transforms up to this length: beyond it (radix-16 turn, 512-thread
-#endif                        // CTAs) they cost registers or L2 bandwidth and measured 3 % slower (r02, profiles/r02_czt_variants.md)
-#ifndef LFD_CZT_L2PRE
-#define LFD_CZT_L2PRE 1       // prefetch.global.L2 of the next unit's input rows
-#endif
-#ifndef LFD_CZT_CONTIG
-#define LFD_CZT_CONTIG 0      // 1: one contiguous run of work units per CTA instead of the round-robin deal (see czt_stage_kernel)
-#endif
-#ifndef LFD_CZT_F64_THREADS
-#define LFD_CZT_F64_THREADS 512
-#endif
-#ifndef LFD_CZT_F32_THREADS
-#define LFD_CZT_F32_THREADS 768
-#endif
-#ifndef LFD_CZT_STAGING
-#define LFD_CZT_STAGING 1     // next unit's input rows copied into shared memory by the bulk-copy engine while this unit computes
-#endif
-#ifndef LFD_CZT_STAGING_MINLG
-#define LFD_CZT_STAGING_MINLG 11   // ... for transforms of at least this length (measured r02: +1 % at 2048, +5 % at 4096, -15 % at 1024)
-#endif
-#ifndef LFD_CZT_PPRE
-#define LFD_CZT_PPRE 4        // post-chirp factors prefetched before the last pass (0 .. 8)
-#endif
-__host__ __device__ constexpr int rows_for(int lg) {
-    return LFD_CZT_ELEMS ? ((1 << lg) >= LFD_CZT_ELEMS ? 1 : LFD_CZT_ELEMS >> lg) : (lg <= 10 ? 2048 >> lg : (lg == 11 ? 2 : 1));
-}
-__host__ __device__ constexpr int cta_threads(int lg) { return ((1 << lg) / 16) * rows_for(lg); }
-__host__ __device__ constexpr int nbuf_for(int lg) { return ((size_t)LFD_CZT_NBUF * rows_for(lg) * ((1 << lg) + (1 << lg) / 16) * 16 > 200 * 1024) ? 1 : LFD_CZT_NBUF; }
-
-__global__ void roots_kernel() {
-    const int lg = MIN_LOG2L + blockIdx.y;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    const int np = nreg(lg);
-    for (int p = 1; p <= np; ++p) {
-        const int Ns = 1 << (4 * p), off = tw_offset(p);
-        if (e >= off && e < off + Ns) {
-            const int k = e - off;
-            const double den = p < np ? 16.0 * Ns : (double)(1 << lg);
-            double s, c;
-            sincospi(-2.0 * (double)k / den, &s, &c);      // k / den is exact (power-of-two denominator)
-            g_tw[blockIdx.y][e] = make_double2(c, s);
-            g_twf[blockIdx.y][e] = make_float2((float)c, (float)s);
-        }
-    }
-}
-
-// complex arrays are complex128 in the FP64 build and complex64 in the FP32 build (type-erased here)
-struct Plane {
-    const void *f; long long ldf;
-    void *Gt;                     // stage A result, transposed: N x mpad
-    void *out; long long ldo;
-    int m, n, M, N, mpad, logLA, logLB, intensity;
-    void *preA, *postA, *HA;      // axis 1 (n -> N): pre[n], post[N], H[LA]
-    void *preB, *postB, *HB;      // axis 0 (m -> M)
-    double alpha_r, alpha_c, x0r, y0r, x0c, y0c, sgn, scale;
-    // fused pupil prep: when amp != NULL, f(i, c) = amp * mask * exp(+2 pi i opd / lambda) at pupil pixel (pr0 + i, pc0 + c)
-    const double *amp, *opd;
-    const unsigned char *mask;
-    long long pld;
-    int pr0, pc0;
-    double wavelength, inv_wavelength;
-};
+__global__ void roots_kernel() { fill_roots(g_tw); }
 
 // ---- the row transform, once per precision ----------------------------------------------------------------------
 namespace f64 {
@@ -153,23 +67,6 @@ __device__ __forceinline__ V2 phasor(double am, double op, double, double inv_la
 }
 #include "mft_czt_body.cuh"
 }  // namespace f64
-
-namespace f32 {
-using RL = float;
-using V2 = float2;
-constexpr int REG_THREADS = LFD_CZT_F32_THREADS;  // threads per SM the register allocation must allow (768 -> 85 registers)
-__device__ __forceinline__ V2 mk2(RL x, RL y) { return make_float2(x, y); }
-__device__ __forceinline__ const V2 *tw_table(int lg) { return g_twf[lg - MIN_LOG2L]; }
-// the phase is still formed and reduced in float64 (it reaches 1e2 .. 1e4 cycles); sine and cosine of the reduced phase in fp32
-__device__ __forceinline__ V2 phasor(double am, double op, double, double inv_lam) {
-    const double tcyc = op * inv_lam;             // one FP64 multiply instead of a division: 1 ulp of the phase in cycles
-    float sn, cs;
-    sincospif((float)(2.0 * (tcyc - rint(tcyc))), &sn, &cs);
-    const float a = (float)am;
-    return make_float2(a * cs, a * sn);
-}
-#include "mft_czt_body.cuh"
-}  // namespace f32
 
 using namespace f64;      // the tables below are always computed in float64 (and rounded once for the complex64 build)
 
@@ -296,27 +193,12 @@ size_t czt_workspace_bytes(const lfd_mft_desc *descs, int count, bool c64) {
     return bytes;
 }
 
-template <class K>
-static int launch_stage(K kernel, int threads, int smem, int total, int dev, int nsm, const Plane *dd, const int *starts, int count,
-                        cudaStream_t stream) {
-    int occ = 1;
-    if (ensure_dynamic_smem(dev, (const void *)kernel, smem)) return 1;
-    LFD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem));
-    LFD_REQUIRE(occ > 0, "lfd_mft (chirp-z): a stage kernel does not fit an SM (%d threads, %d bytes of shared memory)", threads, smem);
-    const int grid = total < nsm * occ ? total : nsm * occ;
-    kernel<<<grid, threads, smem, stream>>>(dd, starts, count);
-    LFD_CUDA_OK(cudaGetLastError());
-    count_launch();
-    return 0;
-}
-
 template <int LOG2L>
 static int launch_for_length(const Plane *dd, int count, const int *starts_a, int total_a, const int *starts_b, int total_b,
                              int phase, int dev, int nsm, bool c64, cudaStream_t stream) {
-    constexpr int L = 1 << LOG2L, ROWS = rows_for(LOG2L), NBUF = nbuf_for(LOG2L), NT = cta_threads(LOG2L);
+    constexpr int L = 1 << LOG2L, NT = cta_threads(LOG2L);
     const int smem_tab = (L + L / 16) * (int)sizeof(double2);                   // the tables are always built in float64
-    const int smem = NBUF * ROWS * (L + L / 16) * (int)(c64 ? sizeof(float2) : sizeof(double2)) +
-                     ((LFD_CZT_STAGING && LOG2L >= LFD_CZT_STAGING_MINLG) ? ROWS * (L / 2 + 4) * 16 : 0);   // + the input staging buffer
+    const int smem = stage_smem_bytes(LOG2L, sizeof(double2));
     if (phase == 0) {
         if (c64) {
             if (ensure_dynamic_smem(dev, (const void *)czt_tables_kernel<LOG2L, float2>, smem_tab)) return 1;
@@ -330,10 +212,10 @@ static int launch_for_length(const Plane *dd, int count, const int *starts_a, in
         return 0;
     }
     if (phase == 1 && total_a > 0)
-        return c64 ? launch_stage(f32::czt_stage_kernel<LOG2L, true>, NT, smem, total_a, dev, nsm, dd, starts_a, count, stream)
+        return c64 ? czt_f32_launch_stage(LOG2L, true, total_a, dev, nsm, dd, starts_a, count, stream)
                    : launch_stage(f64::czt_stage_kernel<LOG2L, true>, NT, smem, total_a, dev, nsm, dd, starts_a, count, stream);
     if (phase == 2 && total_b > 0)
-        return c64 ? launch_stage(f32::czt_stage_kernel<LOG2L, false>, NT, smem, total_b, dev, nsm, dd, starts_b, count, stream)
+        return c64 ? czt_f32_launch_stage(LOG2L, false, total_b, dev, nsm, dd, starts_b, count, stream)
                    : launch_stage(f64::czt_stage_kernel<LOG2L, false>, NT, smem, total_b, dev, nsm, dd, starts_b, count, stream);
     return 0;
 }
@@ -363,6 +245,7 @@ int launch_mft_czt(const lfd_mft_desc *descs, int count, void *workspace, size_t
             if (dev < 64) ready[dev] = true;
         }
     }
+    if (c64 && czt_f32_ensure_roots(dev, stream)) return 1;
 
     const size_t hdr = header_bytes(count);
     char *hbuf = (char *)calloc(hdr, 1);
