@@ -95,12 +95,14 @@ int lfd_mft_c128_batched(const lfd_mft_desc *descs_host, int count,
 int lfd_mft_c128(const lfd_mft_desc *desc_host, void *workspace_dev, size_t workspace_bytes,
                  void *stream);
 
-/* Fused K1 + K2a (folded variant only): the input of plane i is not read from desc.f but formed on the
- * fly as amp * mask * exp(+2 pi i opd / wavelength) over the m x n window at (r0, c0) of the pupil
- * arrays (lentil/plane.py:502-507), so phasors never exist in HBM.  With intensity_out != 0 the result
- * written to desc.out is |F|^2 as float64 (ldo in doubles) instead of the complex field — valid when
- * the plane is the only Field of its wavefront (no coherent merge, lentil/field.py:413-461).
- * Workspace: lfd_mft_workspace_bytes with the folded variant selected. */
+/* Fused K1 + K2a (chirp-z and folded executions; a batch whose execution resolves to DIRECT runs the folded
+ * one): the input of plane i is not read from desc.f but formed on the fly as amp * mask *
+ * exp(+2 pi i opd / wavelength) over the m x n window at (r0, c0) of the pupil arrays
+ * (lentil/plane.py:502-507), so phasors never exist in HBM.  With intensity_out != 0 the result written
+ * to desc.out is |F|^2 as float64 (ldo in doubles) instead of the complex field — valid when the plane
+ * is the only Field of its wavefront (no coherent merge, lentil/field.py:413-461).
+ * Workspace: lfd_mft_workspace_bytes for the same descriptors (with DIRECT: size it with execution = 1 +
+ * LFD_MFT_FOLDED). */
 typedef struct lfd_pupil_src {
     const double  *amp, *opd;     /* dev, n_r x n_c float64                                   */
     const uint8_t *mask;          /* dev, this segment's n_r x n_c mask plane, or NULL         */
