@@ -64,12 +64,27 @@ def plane_flops(m, n, M, N):
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
+    @staticmethod
+    def _stamp(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
 
     def start(self):
         try:
@@ -93,21 +108,32 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        parsed = []
         for r in self.rows:
             parts = [p.strip() for p in r.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
+                parsed.append((self._stamp(parts[0]), float(parts[1]), float(parts[2]),
+                               [n for n, v in zip(names, parts[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nme, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nme)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+
+        def summary(rows):
+            return {"sm_mhz": float(np.median([r[1] for r in rows])) if rows else None,
+                    "sm_max_mhz": max(r[2] for r in rows) if rows else None, "samples": len(rows),
+                    "reasons": sorted({n for r in rows for n in r[3]})}
+        # samples whose nvidia-smi timestamp lies inside the timed region (the sampler runs from before the warm-up, so that it
+        # is up when the region starts); the samples of the whole loaded phase (warm-up included) are summarised beside them
+        inside = [r for r in parsed if r[0] is not None and self.t0 is not None and self.t1 is not None and self.t0 - 0.02 <= r[0] <= self.t1 + 0.02]
+        out = summary(inside)
+        out["timed_region_s"] = None if self.t0 is None or self.t1 is None else self.t1 - self.t0
+        out["under_load_incl_warmup"] = summary(parsed)
+        if not inside and parsed:            # region shorter than nvidia-smi's sampling period: report the loaded phase
+            out.update({k: out["under_load_incl_warmup"][k] for k in ("sm_mhz", "sm_max_mhz", "reasons")})
+            out["note"] = "no nvidia-smi sample fell inside the timed region; values from the loaded phase around it"
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -328,24 +354,26 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up -------------------------------------------------------------------------------
+    # ---- warm-up (the clock sampler is started first: nvidia-smi needs ~0.1 s to deliver its first sample) -----------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(warmup):
         psf = step_resident()
     barrier()
 
     # ---- timed: resident inputs, device time, with K2a and K3 timed on their own ---------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     fourier.TIMERS, lfield.TIMERS = [], []
     launches0 = device.launch_count()
     e0, e1 = _event_pair(torch)
     barrier()
+    sampler.mark_begin()
     e0.record()
     for _ in range(steps):
         psf = step_resident()
     e1.record()
     barrier()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1)
     launches = device.launch_count() - launches0
     mft_ms = sum(t[0].elapsed_time(t[1]) for t in fourier.TIMERS)
