@@ -81,7 +81,7 @@ struct FoldDesc {
     const unsigned char *mask;   // this segment's mask plane, or NULL
     long long pld;               // pupil row stride (n_c)
     int pr0, pc0;
-    double wavelength;
+    double wavelength, inv_wavelength;
 };
 
 __device__ __forceinline__ double2 pupil_phasor(const FoldDesc &d, int i, int c) {
@@ -89,7 +89,7 @@ __device__ __forceinline__ double2 pupil_phasor(const FoldDesc &d, int i, int c)
     double a = d.amp[pix];
     if (d.mask != nullptr && d.mask[pix] == 0) a = 0.0;
     if (a == 0.0) return make_double2(0.0, 0.0);
-    const double tcyc = d.opd[pix] / d.wavelength;      // phase in cycles, reduced exactly
+    const double tcyc = d.opd[pix] * d.inv_wavelength;  // phase in cycles (multiplication by the rounded reciprocal, as in K1), reduced exactly
     double sn, cs;
     cis_unit(tcyc - rint(tcyc), cs, sn);
     return make_double2(a * cs, a * sn);
@@ -588,8 +588,9 @@ int launch_mft_folded(const lfd_mft_desc *descs, int count, void *workspace, siz
             fd.D = nullptr; fd.ldd = 0;
             fd.amp = src[i].amp; fd.opd = src[i].opd; fd.mask = src[i].mask;
             fd.pld = src[i].n_c; fd.pr0 = src[i].r0; fd.pc0 = src[i].c0; fd.wavelength = src[i].wavelength;
+            fd.inv_wavelength = 1.0 / src[i].wavelength;
         } else {
-            fd.amp = nullptr; fd.opd = nullptr; fd.mask = nullptr; fd.pld = 0; fd.pr0 = fd.pc0 = 0; fd.wavelength = 1.0;
+            fd.amp = nullptr; fd.opd = nullptr; fd.mask = nullptr; fd.pld = 0; fd.pr0 = fd.pc0 = 0; fd.wavelength = 1.0; fd.inv_wavelength = 1.0;
         }
         fd.nhm = p.n / 2; fd.ncR2 = cRn; fd.ntile = (Kf2 + FBC / 2 - 1) / (FBC / 2); fd.pad2_ = 0;
         fd.kmax = kmax_dev;

@@ -15,7 +15,7 @@ constexpr int PP_MAX_LAM = 128;
 
 struct PupilPrepParams {
     lfd_segment seg[PP_MAX_SEG];
-    double lam[PP_MAX_LAM];
+    double inv_lam[PP_MAX_LAM];      // 1 / wavelength, rounded once on the host
     int nseg, nlam;
 };
 
@@ -42,7 +42,8 @@ pupil_prep_kernel(const double *__restrict__ amp, const double *__restrict__ opd
         CT *dst = out + sg.out_offset + e;
 #pragma unroll 4
         for (int l = 0; l < P.nlam; ++l) {
-            double tcyc = o / P.lam[l];           // phase in cycles
+            double tcyc = o * P.inv_lam[l];       // phase in cycles (a multiplication by the rounded reciprocal instead of a division:
+                                                  // at most one ulp of the phase, ~1e-16 rad for physical OPDs; the fused loads of K2a do the same)
             double r = tcyc - rint(tcyc);          // exact: |r| <= 0.5
             if constexpr (sizeof(CT) == sizeof(float2)) {
                 // complex64 output: fp32 sine/cosine of the fp64-reduced phase (as in the fused fold of mft_c64.cu)
@@ -88,7 +89,7 @@ static int pupil_prep_impl(bool c64, const double *amp, const double *opd, const
                 long long ne = (long long)P.seg[s].h * P.seg[s].w;
                 if (ne > max_elem) max_elem = ne;
             }
-            for (int l = 0; l < P.nlam; ++l) P.lam[l] = wavelengths[l0 + l];
+            for (int l = 0; l < P.nlam; ++l) P.inv_lam[l] = 1.0 / wavelengths[l0 + l];
             long long bx = (max_elem + 255) / 256;
             if (bx > sm_or_default() * 16) bx = sm_or_default() * 16;  // grid-stride beyond 16 CTAs per SM
             dim3 grid((unsigned)bx, (unsigned)P.nseg);
