@@ -86,12 +86,14 @@ accum_kernel(const lfd_window *__restrict__ wins, int nwin, double *__restrict__
 // Pure HBM streaming: two pixels per thread (16-byte loads), eight planes in flight per thread, window pointers and
 // weights in shared memory.  The sum runs over v in the same order and with the same contraction as accum_kernel, so
 // both paths give bit-identical images.
-// FIELDS: the windows are dense full-frame complex128 fields, one per wavefront (nothing to merge coherently): out += sum_v w_v
-// |E_v|^2, one pixel per thread — what the per-wavelength drop-in loop (Wavefront.insert of a single-Field wavefront) produces.
+// FIELDS: the windows are dense complex128 fields that all cover the SAME rectangle of the output, one per wavefront (nothing
+// to merge coherently): out[rect] += sum_v w_v |E_v|^2, one pixel per thread — what the per-wavelength drop-in loop produces
+// (Wavefront.insert of a single-Field wavefront) and what a field point of a multi-field-point batch accumulates per chunk.
 constexpr int FULL_CHUNK = 512;      // windows per launch of the fast path (one accumulation per pixel, as in accum_kernel); more -> generic path
 template <bool FIELDS>
 __global__ void __launch_bounds__(256)
-accum_full_kernel(const lfd_window *__restrict__ wins, int nwin, double *__restrict__ out, long long npairs) {
+accum_full_kernel(const lfd_window *__restrict__ wins, int nwin, double *__restrict__ out, long long npairs,
+                  int r0 = 0, int c0 = 0, int w = 0, long long ldo = 0) {
     __shared__ const double2 *sE[FULL_CHUNK];
     __shared__ double sw[FULL_CHUNK];
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -118,7 +120,8 @@ accum_full_kernel(const lfd_window *__restrict__ wins, int nwin, double *__restr
                     const double2 x = __ldcs(sE[v] + e);
                     a += sw[v] * (x.x * x.x + x.y * x.y);
                 }
-                out[e] += a;
+                const long long rr = e / w;                    // pixel e of the (dense, ld = w) windows -> output (r0 + rr, c0 + cc)
+                out[(r0 + rr) * ldo + c0 + (e - rr * w)] += a;
                 continue;
             }
             double a0 = 0.0, a1 = 0.0;
@@ -141,14 +144,20 @@ accum_full_kernel(const lfd_window *__restrict__ wins, int nwin, double *__restr
     }
 }
 
-// kind 2: float64 intensity planes; kind 0: complex128 fields, every window its own wavefront (strictly increasing groups)
+// kind 2: dense full-frame float64 intensity planes; kind 0: dense complex128 fields on one common rectangle inside the
+// output, every window its own wavefront (strictly increasing groups)
 static bool all_full_frame(const lfd_window *wins, int nwin, const void *out, int H, int W, int64_t ldo, int kind) {
-    if (nwin > FULL_CHUNK || ldo != W || ((uintptr_t)out & 15)) return false;
-    if (kind == 2 && (((long long)H * W) & 1)) return false;
+    if (nwin > FULL_CHUNK || ((uintptr_t)out & 15)) return false;
+    if (kind == 2 && (ldo != W || (((long long)H * W) & 1))) return false;
     for (int v = 0; v < nwin; ++v) {
         const lfd_window &w = wins[v];
-        if (w.c64 != kind || w.r0 != 0 || w.c0 != 0 || w.h != H || w.w != W || w.ld != W || ((uintptr_t)w.E & 15)) return false;
-        if (kind == 0 && v > 0 && w.group <= wins[v - 1].group) return false;
+        if (w.c64 != kind || w.ld != w.w || ((uintptr_t)w.E & 15)) return false;
+        if (kind == 2 && (w.r0 != 0 || w.c0 != 0 || w.h != H || w.w != W)) return false;
+        if (kind == 0) {
+            if (w.r0 < 0 || w.c0 < 0 || w.r0 + w.h > H || w.c0 + w.w > W) return false;
+            if (w.r0 != wins[0].r0 || w.c0 != wins[0].c0 || w.h != wins[0].h || w.w != wins[0].w) return false;
+            if (v > 0 && w.group <= wins[v - 1].group) return false;
+        }
     }
     return true;
 }
@@ -173,12 +182,13 @@ static int launch_accum(bool intensity, const lfd_window *wins, int32_t nwin, vo
     const bool planes = intensity && all_full_frame(wins, nwin, out, H, W, ldo, 2);
     const bool fields = intensity && !planes && all_full_frame(wins, nwin, out, H, W, ldo, 0);
     if (planes || fields) {
-        const long long nelem = planes ? (long long)H * W / 2 : (long long)H * W;
+        const long long nelem = planes ? (long long)H * W / 2 : (long long)wins[0].h * wins[0].w;
         long long blocks = (nelem + 255) / 256;
         const long long cap = (long long)sm_or_default() * 8;
         if (blocks > cap) blocks = cap;
         if (planes) accum_full_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>((const lfd_window *)scratch, nwin, (double *)out, nelem);
-        else accum_full_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>((const lfd_window *)scratch, nwin, (double *)out, nelem);
+        else accum_full_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>((const lfd_window *)scratch, nwin, (double *)out, nelem,
+                                                                           wins[0].r0, wins[0].c0, wins[0].w, (long long)ldo);
         LFD_CUDA_OK(cudaGetLastError());
         count_launch();
         return 0;
